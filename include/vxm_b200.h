@@ -1,0 +1,161 @@
+/*
+ * vxm_b200 — C ABI of the B200-native VxmDense registration path.
+ *
+ * Drop-in boundary.  The reference (voxelmorph/voxelmorph, torch backend) has no FFI
+ * layer of its own: its hot path bottoms out in PyTorch operators (F.grid_sample,
+ * F.interpolate, nn.Conv3d, F.conv3d, torch.optim.Adam).  Each entry point below
+ * replaces one of those call sites; the reference file:line it stands in for is cited
+ * on the declaration.  The host side that binds them (ctypes) is
+ * voxelmorph_b200/_lib.py; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only: every pointer is a DEVICE pointer owned by the caller
+ *    (PyTorch caching allocator); the library allocates nothing persistent;
+ *  - tensors are contiguous, float32, batch-major "NCDHW" (B, C, D, H, W) unless a
+ *    declaration says otherwise; a 2-D problem is passed with D == 1 and nd == 2
+ *    (flows then carry 2 channels: H, W);
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*); no implicit
+ *    synchronisation; the current CUDA device is the caller's;
+ *  - return value 0 on success, negative on error; vxm_last_error() gives the text
+ *    (thread local).  Nothing throws or aborts;
+ *  - `*_workspace_bytes` functions are pure host arithmetic (no CUDA calls).
+ */
+#ifndef VXM_B200_H
+#define VXM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VXM_OK 0
+#define VXM_ERR_ARG (-1)
+#define VXM_ERR_CUDA (-2)
+#define VXM_ERR_UNSUPPORTED (-3)
+
+/* interpolation mode of the resampler (reference SpatialTransformer(mode=...), layers.py:11-14) */
+#define VXM_MODE_LINEAR 0
+#define VXM_MODE_NEAREST 1
+/* how `loc / (S-1)` of layers.py:37 is rounded: a true fp32 division (torch CPU) or a
+ * multiply by fl(1/(S-1)) (what torch's CUDA `tensor / python_scalar` computes). */
+#define VXM_ARITH_TRUE_DIV 0
+#define VXM_ARITH_RECIPROCAL 1
+
+const char* vxm_last_error(void);
+/* library / build identification ("vxm_b200 <version> sm_100a") */
+const char* vxm_version(void);
+/* number of kernel launches issued through this library by the calling process so far */
+uint64_t vxm_launch_count(void);
+
+/* ---- SpatialTransformer: reference voxelmorph/torch/layers.py:30-48 (F.grid_sample :48) ----
+ * out[b,c,p] = sample(src[b,c], p + flow[b,:,p]); zeros padding; align_corners=True.
+ * src: (B,C,Ds,Hs,Ws)  flow: (B,nd,D,H,W)  out: (B,C,D,H,W).  The reference always uses
+ * (Ds,Hs,Ws) == (D,H,W); distinct sizes follow grid_sample's semantics. */
+int vxm_warp_fwd(const float* src, const float* flow, float* out,
+                 int B, int C, int Ds, int Hs, int Ws, int D, int H, int W, int nd,
+                 int mode, int arith, void* stream);
+/* backward of the above.  grad_src (B,C,Ds,Hs,Ws) is ACCUMULATED into (caller zero-fills) and
+ * may be NULL; grad_flow (B,nd,D,H,W) is overwritten and may be NULL. */
+int vxm_warp_bwd(const float* grad_out, const float* src, const float* flow,
+                 float* grad_src, float* grad_flow,
+                 int B, int C, int Ds, int Hs, int Ws, int D, int H, int W, int nd,
+                 int mode, int arith, void* stream);
+
+/* ---- VecInt: reference voxelmorph/torch/layers.py:51-68 (scaling and squaring) ----
+ * vel, out: (B,nd,D,H,W).  All nsteps squarings run in one cooperative launch.
+ * If `states` is non-NULL it receives the nsteps intermediate fields v_0..v_{n-1}
+ * (nsteps * B*nd*D*H*W floats) needed by the backward; otherwise `work` must hold
+ * vxm_vecint_workspace_bytes() bytes of scratch. */
+size_t vxm_vecint_workspace_bytes(int B, int D, int H, int W, int nd, int nsteps);
+int vxm_vecint_fwd(const float* vel, float* out, float* states, void* work,
+                   int B, int D, int H, int W, int nd, int nsteps, int arith, void* stream);
+/* grad_vel (B,nd,D,H,W) overwritten.  `states` as written by the forward; `work` holds
+ * 2 * B*nd*D*H*W floats of scratch. */
+int vxm_vecint_bwd(const float* grad_out, const float* states, float* grad_vel, void* work,
+                   int B, int D, int H, int W, int nd, int nsteps, int arith, void* stream);
+
+/* ---- ResizeTransform: reference voxelmorph/torch/layers.py:85-97 (F.interpolate :88,:94) ----
+ * out = post * lerp(pre * x) with align_corners=True linear interpolation.
+ * x: (B,C,Di,Hi,Wi)  out: (B,C,Do,Ho,Wo). */
+int vxm_resize_fwd(const float* x, float* out, int B, int C, int Di, int Hi, int Wi,
+                   int Do, int Ho, int Wo, float pre, float post, void* stream);
+/* adjoint (deterministic gather form).  grad_x overwritten. */
+int vxm_resize_bwd(const float* grad_out, float* grad_x, int B, int C, int Di, int Hi, int Wi,
+                   int Do, int Ho, int Wo, float pre, float post, void* stream);
+
+/* ---- NCC: reference voxelmorph/torch/losses.py:15-67 (5 x F.conv3d with a ones filter) ----
+ * I = y_true, J = y_pred: (B,1,D,H,W).  win = (wd,wh,ww) odd window (1 along D for 2-D).
+ * loss[0] = -mean(cc).  `work`: vxm_ncc_workspace_bytes().  If `saved` is non-NULL the
+ * forward stores 4 fields (4 * B*D*H*W floats) that the backward consumes. */
+size_t vxm_ncc_workspace_bytes(int B, int D, int H, int W);
+int vxm_ncc_fwd(const float* I, const float* J, float* loss, float* saved, void* work,
+                int B, int D, int H, int W, int wd, int wh, int ww, void* stream);
+/* grad_J = grad_loss[0] * d(-mean cc)/dJ.  grad_loss is a device scalar. */
+int vxm_ncc_bwd(const float* I, const float* J, const float* saved, const float* grad_loss,
+                float* grad_J, int B, int D, int H, int W, int wd, int wh, int ww, void* stream);
+
+/* ---- Grad: reference voxelmorph/torch/losses.py:102-135 ----
+ * y: (B,nd,D,H,W) (any channel count C).  penalty 1 = l1, 2 = l2.  loss[0] = mult * mean_b mean_axes mean |dy|^p */
+size_t vxm_reduce_workspace_bytes(void);
+int vxm_gradloss_fwd(const float* y, float* loss, void* work, int B, int C, int D, int H, int W,
+                     int nd, int penalty, float mult, void* stream);
+int vxm_gradloss_bwd(const float* y, const float* grad_loss, float* grad_y, int B, int C, int D,
+                     int H, int W, int nd, int penalty, float mult, void* stream);
+
+/* ---- MSE: reference voxelmorph/torch/losses.py:75-76 ---- */
+int vxm_mse_fwd(const float* y_true, const float* y_pred, float* loss, void* work, size_t n,
+                void* stream);
+int vxm_mse_bwd(const float* y_true, const float* y_pred, const float* grad_loss,
+                float* grad_pred, size_t n, void* stream);
+
+/* ---- Dice: reference voxelmorph/torch/losses.py:84-90 ----
+ * y_true, y_pred: (B,L,V) with V = D*H*W.  `work`: vxm_dice_workspace_bytes(B*L).
+ * `sums` (2*B*L floats: top, bottom(unclamped)) is written for the backward. */
+size_t vxm_dice_workspace_bytes(int BL);
+int vxm_dice_fwd(const float* y_true, const float* y_pred, float* loss, float* sums, void* work,
+                 int BL, size_t V, void* stream);
+int vxm_dice_bwd(const float* y_true, const float* sums, const float* grad_loss, float* grad_pred,
+                 int BL, size_t V, void* stream);
+
+/* ---- Conv3d k=3 s=1 p=1 (+bias, +LeakyReLU 0.2): reference voxelmorph/torch/networks.py:299-304
+ * (ConvBlock), :211,:257 (flow head, no activation).  fp32 "parity" engine, NCDHW.
+ * x: (B,Cin,D,H,W)  w: (Cout,Cin,kd,3,3) with kd = 3 (3-D) or 1 (2-D)  y: (B,Cout,D,H,W).
+ * leaky_slope < 0 disables the activation. */
+int vxm_conv3d_fwd_f32(const float* x, const float* w, const float* bias, float* y,
+                       int B, int Cin, int Cout, int D, int H, int W, int kd,
+                       float leaky_slope, void* stream);
+/* grad_y is the gradient w.r.t. the ACTIVATED output y; y (saved forward output) supplies the
+ * LeakyReLU mask (y < 0).  grad_x may be NULL (first layer).  grad_w / grad_b are ACCUMULATED
+ * into (caller zero-fills once per step).  work: vxm_conv3d_bwd_workspace_bytes(). */
+size_t vxm_conv3d_bwd_workspace_bytes(int B, int Cin, int Cout, int D, int H, int W, int kd);
+int vxm_conv3d_bwd_f32(const float* grad_y, const float* y, const float* x, const float* w,
+                       float* grad_x, float* grad_w, float* grad_b, void* work,
+                       int B, int Cin, int Cout, int D, int H, int W, int kd,
+                       float leaky_slope, void* stream);
+
+/* ---- MaxPool(2) / nearest Upsample(2) + concat: reference networks.py:83-85,130,137-138 ----
+ * pool factor is 2 on H, W and on D when D > 1 (nd == 3).  idx (uint8, same shape as y) stores the
+ * argmax within the window for the backward. */
+int vxm_maxpool2_fwd(const float* x, float* y, uint8_t* idx, int B, int C, int D, int H, int W,
+                     int nd, void* stream);
+int vxm_maxpool2_bwd(const float* grad_y, const uint8_t* idx, float* grad_x, int B, int C, int D,
+                     int H, int W, int nd, void* stream);
+/* out (B, Ca+Cb, 2D,2H,2W) = cat(upsample2(a (B,Ca,D,H,W)), skip (B,Cb,2D,2H,2W)); skip may be NULL (Cb=0) */
+int vxm_upcat_fwd(const float* a, const float* skip, float* out, int B, int Ca, int Cb, int D,
+                  int H, int W, int nd, void* stream);
+/* grad_a overwritten (sum over the 2^nd children), grad_skip overwritten (may be NULL) */
+int vxm_upcat_bwd(const float* grad_out, float* grad_a, float* grad_skip, int B, int Ca, int Cb,
+                  int D, int H, int W, int nd, void* stream);
+
+/* ---- Adam on one flat buffer: reference scripts/torch/train.py:161,220 (torch.optim.Adam) ----
+ * p, g, m, v: n floats.  grad_scale multiplies g first (1/world_size after an allreduce-sum). */
+int vxm_adam_step(float* p, const float* g, float* m, float* v, size_t n, int step, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VXM_B200_H */

@@ -1,0 +1,112 @@
+"""GPU parity tests of the whole VxmDense path (every ctor variant of SURVEY.md section 8(a) A1) against the
+golden vectors frozen from the unmodified reference, plus checkpoint interchange."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases, ref_torch
+
+from test_oracle import VARIANTS, full_cfg
+
+pytestmark = pytest.mark.gpu
+REL = 1e-4
+
+
+def t(x):
+    return torch.from_numpy(np.ascontiguousarray(x))
+
+
+def rel_err(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+@pytest.fixture(scope="module")
+def vxm(cuda):
+    import voxelmorph_b200 as v
+    v._lib.load()
+    return v
+
+
+@pytest.mark.parametrize("name", sorted(VARIANTS))
+def test_vxmdense_forward_and_train_step(vxm, cuda, golden, name):
+    g = golden("vxmdense")
+    kw = VARIANTS[name]
+    cfg = full_cfg(kw)
+    model = vxm.networks.VxmDense(**kw)
+    assert model.config == cfg
+    sd = ref_torch.init_state_dict(cfg, seed=1234, flow_std=2e-2)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not missing and not unexpected
+    model.to(cuda)
+    shape = kw["inshape"]
+    s, tr = cases.volume_pair(91, shape, sigma=1.5)
+    S, T = t(s).to(cuda), t(tr).to(cuda)
+    with torch.no_grad():
+        out = model(S, T)
+        reg = model(S, T, registration=True)
+    nout = 3 if cfg["bidir"] else 2
+    assert len(out) == nout
+    for i, y in enumerate(out):
+        ref = g["%s/train%d" % (name, i)]
+        assert tuple(y.shape) == ref.shape
+        assert rel_err(y.cpu().numpy(), ref) <= REL, (name, i)
+    assert rel_err(reg[1].cpu().numpy(), g["%s/reg_flow" % name]) <= REL
+    assert torch.equal(reg[0], out[0])
+
+    # one training step, as scripts/torch/train.py:204-220
+    model.train()
+    nd = len(shape)
+    use_ncc = nd == 3 and name != "nodiffeo3d"
+    img = vxm.losses.NCC().loss if use_ncc else vxm.losses.MSE().loss
+    losses = [img, img] if cfg["bidir"] else [img]
+    weights = [0.5, 0.5] if cfg["bidir"] else [1]
+    losses += [vxm.losses.Grad("l2", loss_mult=cfg["int_downsize"]).loss]
+    weights += [0.01]
+    y_true = [T, S, None] if cfg["bidir"] else [T, None]
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    y_pred = model(S, T)
+    loss = 0
+    for n, fn in enumerate(losses):
+        loss = loss + fn(y_true[n], y_pred[n]) * weights[n]
+    opt.zero_grad()
+    loss.backward()
+    ref_loss = float(g["%s/loss" % name])
+    assert abs(float(loss.item()) - ref_loss) <= REL * abs(ref_loss), name
+    params = dict(model.named_parameters())
+    gtol = 2e-3 if use_ncc else 2e-4     # the fp32 reference's own NCC backward is ~1e-3 from fp64 (see test_gpu_ops)
+    for k in ("flow.weight", "flow.bias", "unet_model.encoder.0.0.main.weight", "unet_model.decoder.0.0.main.weight",
+              "unet_model.remaining.0.main.bias"):
+        key = "%s/grad/%s" % (name, k)
+        if key in g:
+            assert rel_err(params[k].grad.cpu().numpy(), g[key]) <= gtol, (name, k)
+    opt.step()
+    for k in ("flow.weight", "unet_model.encoder.0.0.main.weight"):
+        assert rel_err(params[k].detach().cpu().numpy(), g["%s/after/%s" % (name, k)]) <= 1e-3, (name, k)
+
+
+def test_checkpoint_interchange(vxm, cuda, tmp_path):
+    """save() writes the reference's {'config','model_state'} format; a reference-style file (with .grid
+    buffers in it) loads; the forward output survives a round trip bit for bit."""
+    kw = dict(inshape=(16, 16, 16), nb_unet_features=[[4, 8, 8, 8], [8, 8, 8, 8, 8, 4, 4]])
+    m = vxm.networks.VxmDense(**kw).to(cuda)
+    p = str(tmp_path / "m.pt")
+    m.save(p)
+    ck = torch.load(p, map_location="cpu")
+    assert set(ck) == {"config", "model_state"} and not any(k.endswith(".grid") for k in ck["model_state"])
+    ck["model_state"]["transformer.grid"] = torch.zeros(1, 3, 16, 16, 16)          # as a reference checkpoint may carry
+    ck["model_state"]["integrate.transformer.grid"] = torch.zeros(1, 3, 8, 8, 8)
+    torch.save(ck, p)
+    m2 = vxm.networks.VxmDense.load(p, "cuda")
+    m2.to(cuda)
+    s, tr = cases.volume_pair(5, (16, 16, 16))
+    with torch.no_grad():
+        a = m(t(s).to(cuda), t(tr).to(cuda))
+        b = m2(t(s).to(cuda), t(tr).to(cuda))
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+def test_use_probs_raises(vxm):
+    with pytest.raises(NotImplementedError):
+        vxm.networks.VxmDense((16, 16, 16), use_probs=True)
