@@ -112,7 +112,7 @@ def test_warp_full_size_digest_and_properties(vxm, cuda):
     zero = torch.zeros(1, 3, *full, device=cuda)
     assert torch.equal(stn(g2(lab, cuda), zero).cpu(), t(lab))
     v = g2(vol, cuda)
-    assert float((st(v, zero) - v).abs().max()) < 2e-6
+    assert float((st(v, zero) - v).abs().max()) < 2e-5   # coordinate round trip is exact only to ~S*2^-24 voxels
     f = g2(flow, cuda)
     a = st(v, f)
     b = st(2 * v, f)
