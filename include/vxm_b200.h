@@ -135,6 +135,26 @@ int vxm_conv3d_bwd_f32(const float* grad_y, const float* y, const float* x, cons
                        int B, int Cin, int Cout, int D, int H, int W, int kd,
                        float leaky_slope, void* stream);
 
+/* ---- Conv3d k=3 on tcgen05 tensor cores (bf16 operands, fp32 TMEM accumulation), channels-last ----
+ * The throughput engine for reference networks.py:299-304 / :211,257; forward and dgrad share one kernel.
+ * Activations are bf16 NDHWC (B,D,H,W,C).  Weights are pre-packed by vxm_conv3d_tc_pack into the UMMA
+ * canonical K-major layout [tap][K/16][2][N][8] (bf16); `transposed` = 1 packs the dgrad operator
+ * (channel roles swapped, taps flipped).  np = MMA N (16 or 32) >= number of output channels. */
+size_t vxm_conv3d_tc_packed_bytes(int cin_eff, int np, int kd);
+int vxm_conv3d_tc_pack(const float* w, void* wpk, int Cout, int Cin, int kd, int np, int transposed,
+                       void* stream);
+/* Input = channel concat of [xa (Ca ch; at HALF resolution and nearest-upsampled x2 on the fly when up=1),
+ * xb (Cb ch)], both bf16 NDHWC; or, when nplanar > 0, `nplanar` (<= 4) planar fp32 volumes xf[i]
+ * ((B,D,H,W) each, batch stride xf_bstride[i] floats) converted on load (first layer: source/target images;
+ * flow-head dgrad: the 3 flow-gradient planes).  out_mode 0: bf16 NDHWC (B,D,H,W,Cout), Cout % 8 == 0;
+ * out_mode 1: fp32 NCDHW.  Epilogue: + bias (may be NULL), then LeakyReLU(slope) if slope >= 0; if `mask`
+ * (bf16 NDHWC, same shape as out) is given the activation is replaced by  out *= (mask < 0 ? slope : 1)
+ * (LeakyReLU derivative of the layer below, for dgrad). */
+int vxm_conv3d_tc_fwd(const void* xa, const void* xb, const float* const* xf, const long long* xf_bstride,
+                      int nplanar, const void* wpk, const float* bias, void* out, const void* mask,
+                      int B, int D, int H, int W, int Ca, int Cb, int up, int Cout, int np, int kd,
+                      int out_mode, float slope, void* stream);
+
 /* ---- MaxPool(2) / nearest Upsample(2) + concat: reference networks.py:83-85,130,137-138 ----
  * pool factor is 2 on H, W and on D when D > 1 (nd == 3).  idx (uint8, same shape as y) stores the
  * argmax within the window for the backward. */

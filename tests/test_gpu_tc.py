@@ -1,0 +1,101 @@
+"""GPU parity tests of the tcgen05 (bf16 operands, fp32 TMEM accumulation) convolution engine against the CPU
+oracle evaluated on the SAME bf16-rounded operands (fp64 accumulation).  Tolerances: bf16-output paths 1e-2 of
+max|ref| (output rounding is 2^-9 relative), fp32-output paths 1e-4."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    a = a.double()
+    b = b.double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+@pytest.fixture(scope="module")
+def tc(cuda):
+    import voxelmorph_b200 as v
+    from voxelmorph_b200 import tc
+    v._lib.load()
+    return tc
+
+
+CASES = [
+    # shape, Ca, Cb, up, Cout
+    ((4, 16, 8), 16, 0, False, 16),
+    ((20, 40, 24), 32, 0, False, 32),
+    ((10, 12, 14), 32, 0, False, 32),     # ragged tiles (coarsest U-Net level shape)
+    ((8, 32, 16), 32, 16, True, 32),      # nearest-x2 upsample + skip concat fused in the loader (48 -> 32)
+    ((8, 16, 16), 32, 32, True, 32),      # 64 -> 32
+    ((6, 16, 24), 32, 0, False, 16),
+    ((1, 32, 24), 16, 0, False, 32),      # 2-D (kd = 1)
+]
+
+
+@pytest.mark.parametrize("shape,Ca,Cb,up,Cout", CASES)
+def test_tc_conv_forward(tc, cuda, shape, Ca, Cb, up, Cout):
+    g = torch.Generator().manual_seed(hash((shape, Ca, Cb)) % 1000)
+    kd = 1 if shape[0] == 1 else 3
+    D, H, W = shape
+    ashape = ((D // 2 if kd == 3 else D), H // 2, W // 2) if up else shape
+    xa = bf(torch.randn((2, Ca) + ashape, generator=g))
+    xb = bf(torch.randn((2, Cb) + shape, generator=g)) if Cb else None
+    w = bf(torch.randn((Cout, Ca + Cb, kd, 3, 3), generator=g) * 0.1)
+    b = torch.randn(Cout, generator=g)
+    xin = xa
+    if up:
+        xin = F.interpolate(xa, scale_factor=(2 if kd == 3 else 1, 2, 2), mode="nearest")
+    if xb is not None:
+        xin = torch.cat([xin, xb], dim=1)
+    ref = F.leaky_relu(F.conv3d(xin.double(), w.double(), b.double(), padding=(kd // 2, 1, 1)), 0.2)
+    wpk, NP = tc.pack_weights(w.to(cuda))
+    out = tc.conv_fwd(tc.to_ndhwc_bf16(xa.to(cuda)), None if xb is None else tc.to_ndhwc_bf16(xb.to(cuda)), wpk, NP,
+                      b.to(cuda), Cout, kd, up=up, slope=0.2)
+    torch.cuda.synchronize()
+    assert rel_err(tc.from_ndhwc(out).cpu(), ref) <= 1e-2
+
+
+def test_tc_flow_head_fp32_out(tc, cuda):
+    g = torch.Generator().manual_seed(5)
+    x = bf(torch.randn((1, 16, 12, 20, 16), generator=g))
+    w = bf(torch.randn((3, 16, 3, 3, 3), generator=g) * 0.05)
+    b = torch.randn(3, generator=g) * 0.1
+    ref = F.conv3d(x.double(), w.double(), b.double(), padding=1)
+    wpk, NP = tc.pack_weights(w.to(cuda))
+    out = tc.conv_fwd(tc.to_ndhwc_bf16(x.to(cuda)), None, wpk, NP, b.to(cuda), 3, 3, out_fp32_planar=True)
+    assert rel_err(out.cpu(), ref) <= 1e-4
+
+
+def test_tc_first_layer_planar_fp32_inputs(tc, cuda):
+    g = torch.Generator().manual_seed(6)
+    src, trg = torch.rand((2, 1, 8, 24, 16), generator=g), torch.rand((2, 1, 8, 24, 16), generator=g)
+    w = bf(torch.randn((16, 2, 3, 3, 3), generator=g) * 0.2)
+    b = torch.randn(16, generator=g) * 0.1
+    ref = F.leaky_relu(F.conv3d(bf(torch.cat([src, trg], 1)).double(), w.double(), b.double(), padding=1), 0.2)
+    wpk, NP = tc.pack_weights(w.to(cuda))
+    out = tc.conv_fwd(None, None, wpk, NP, b.to(cuda), 16, 3, planar=[src.to(cuda), trg.to(cuda)], slope=0.2)
+    assert rel_err(tc.from_ndhwc(out).cpu(), ref) <= 1e-2
+
+
+def test_tc_dgrad_with_mask(tc, cuda):
+    """dgrad = the same kernel on the transposed / flipped packed weights; the LeakyReLU derivative of the layer
+    below is applied in the epilogue from its saved (bf16) activation."""
+    g = torch.Generator().manual_seed(7)
+    Cin, Cout, shape = 32, 16, (6, 16, 16)
+    x = torch.randn((1, Cin) + shape, generator=g, dtype=torch.float64, requires_grad=True)
+    w = bf(torch.randn((Cout, Cin, 3, 3, 3), generator=g) * 0.1)
+    gy = bf(torch.randn((1, Cout) + shape, generator=g))
+    F.conv3d(x, w.double(), None, padding=1).backward(gy.double())
+    below = bf(torch.randn((1, Cin) + shape, generator=g))          # activation of the layer below (mask source)
+    ref = x.grad * torch.where(below.double() < 0, 0.2, 1.0)
+    wpk, NP = tc.pack_weights(w.to(cuda), transposed=True)
+    out = tc.conv_fwd(tc.to_ndhwc_bf16(gy.to(cuda)), None, wpk, NP, None, Cin, 3, slope=0.2,
+                      mask=tc.to_ndhwc_bf16(below.to(cuda)))
+    assert rel_err(tc.from_ndhwc(out).cpu(), ref) <= 1e-2

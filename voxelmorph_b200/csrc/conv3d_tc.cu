@@ -1,0 +1,372 @@
+// Conv3d k=3 s=1 p=1 as an implicit GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in
+// TMEM) — the throughput engine behind reference voxelmorph/torch/networks.py:299-304 (ConvBlock) and
+// :211,257 (flow head).  Forward and dgrad share this kernel (dgrad = same convolution with swapped
+// channel roles and flipped taps, see vxm_conv3d_tc_pack).
+//
+// Formulation (per output d-slice of a 16 x 8 (h x w) tile):
+//     D[128 voxels x N=Cout] += A_tap[128 voxels x 16 ch] * W_tap[N x 16 ch]        27 taps x Cin/16 K-steps
+//   * activations are bf16, channels-last (NDHWC); a halo'd slab of each input slice, (16+2) x (8+2) voxels,
+//     is staged in shared memory as [Cin/8][180 rows][8 ch] = the UMMA "K-major, no swizzle" canonical
+//     layout (core matrix = 8 voxels x 16 B).  In that layout a tap shift (kh, kw) is just a start-address
+//     offset of (kh*10 + kw) * 16 bytes, so all 9 in-plane taps read the SAME staged slab, and the 3 kd taps
+//     read the 3 resident slabs of a 4-deep ring that slides along D: every input voxel is fetched from
+//     L2/HBM ~1.4x, not 27x.
+//   * weights: bf16, pre-packed per (tap, K-step) into the canonical K-major layout; the whole filter bank
+//     stays resident in shared memory, loaded once per CTA with bulk-TMA copies (cp.async.bulk + mbarrier tx).
+//   * warp-specialised persistent CTA: warps 5-8 stage slabs with zero-filling cp.async (padding, nearest-x2
+//     upsample and the channel concat with the skip tensor are all address arithmetic in the loader — the
+//     48/64-channel concat tensor of networks.py:138 is never materialised); one elected thread of warp 4
+//     issues tcgen05.mma and tcgen05.commit; warps 0-3 drain TMEM (tcgen05.ld: one voxel's Cout channels per
+//     thread), add bias, apply LeakyReLU (or the dgrad mask) and write 16-byte bf16 NDHWC vectors.
+//     Pipelines: slab ring full/empty mbarriers (loader <-> MMA), TMEM full/empty (MMA <-> epilogue).
+#include "tc_common.cuh"
+
+namespace vxm {
+namespace tc {
+
+constexpr int TH = 16, TW = 8;
+constexpr int SW = TW + 2, SH = TH + 2;
+constexpr int ROWS = SH * SW;     // 180 voxels per channel-chunk plane
+constexpr int PLANE = ROWS * 16;  // bytes
+constexpr int NSLOT = 4, NACC = 2;
+constexpr int NLOADER = 128, NTHREADS = 288;
+
+struct ConvTcArgs {
+  const __nv_bfloat16* xa;    // bf16 NDHWC source A (B,Da,Ha,Wa,Ca); half resolution when up == 1
+  const __nv_bfloat16* xb;    // bf16 NDHWC source B (B,D,H,W,Cb) or null
+  const float* xf[4];         // planar fp32 sources (each (B,1,D,H,W)-like planes), nplanar of them, when Ca == 0
+  long long xf_bstride[4];    // batch stride of each planar source in floats
+  int nplanar;
+  const __nv_bfloat16* wpk;   // packed weights
+  const float* bias;
+  void* out;
+  const __nv_bfloat16* mask;  // optional bf16 NDHWC (B,D,H,W,Cout): out *= (mask < 0 ? slope : 1), no activation
+  int B, D, H, W;
+  int Ca, Cb, up, upd;
+  int Cout, NP, KD, out_mode;
+  float slope;
+  int tiles_h, tiles_w, dchunk, nchunks, nitems;
+  uint32_t wbytes;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const ConvTcArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const bool planar = a.nplanar > 0;
+  const int Cin = planar ? 16 : a.Ca + a.Cb;
+  const int nk16 = Cin / 16;
+  const int nc8 = planar ? 1 : Cin / 8;            // staged planes (planar mode: plane 0 data + a shared zero plane)
+  const uint32_t slab_bytes = (uint32_t)nc8 * PLANE;
+  uint8_t* s_w = smem;
+  uint8_t* s_slab = smem + ((a.wbytes + 127u) & ~127u);
+  uint8_t* s_zero = s_slab + NSLOT * slab_bytes;   // one all-zero plane (only used in planar mode)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_zero + PLANE);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + NSLOT;
+  uint64_t* tfull = bars + 2 * NSLOT;
+  uint64_t* tempty = tfull + NACC;
+  uint64_t* wbar = tempty + NACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tmem_cols = (NACC * a.NP <= 32) ? 32u : ((NACC * a.NP <= 64) ? 64u : 128u);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSLOT; ++i) { mbar_init(&full[i], NLOADER); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+    mbar_init(wbar, 1);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < PLANE / 16; i += NTHREADS) reinterpret_cast<uint4*>(s_zero)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (warp == 4) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (threadIdx.x == 0) {  // weights: bulk TMA copies, one mbarrier transaction
+    mbar_expect_tx(wbar, a.wbytes);
+    for (uint32_t off = 0; off < a.wbytes; off += 16384u) {
+      uint32_t n = a.wbytes - off < 16384u ? a.wbytes - off : 16384u;
+      bulk_g2s(s_w + off, reinterpret_cast<const uint8_t*>(a.wpk) + off, n, wbar);
+    }
+  }
+
+  const int HW_tiles = a.tiles_h * a.tiles_w;
+
+  if (warp >= 5) {
+    // ================================ LOADER (128 threads) ================================
+    const int lt = threadIdx.x - 5 * 32;
+    uint32_t cnt = 0;
+    int prev_slot = -1;
+    const int Da = a.upd ? a.D >> 1 : a.D, Ha = a.up ? a.H >> 1 : a.H, Wa = a.up ? a.W >> 1 : a.W;
+    const int nca8 = a.Ca >> 3;
+    for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+      const int wt = item % a.tiles_w, ht = (item / a.tiles_w) % a.tiles_h;
+      const int ch = (item / HW_tiles) % a.nchunks, b = item / (HW_tiles * a.nchunks);
+      const int h0 = ht * TH, w0 = wt * TW, d0 = ch * a.dchunk, d1 = min(d0 + a.dchunk, a.D);
+      const int s_begin = a.KD == 3 ? d0 - 1 : d0, s_end = a.KD == 3 ? d1 + 1 : d1;
+      for (int ds = s_begin; ds < s_end; ++ds) {
+        const int slot = cnt % NSLOT;
+        mbar_wait(&empty[slot], ((cnt / NSLOT) & 1) ^ 1);
+        uint8_t* slab = s_slab + (size_t)slot * slab_bytes;
+        const bool dok = ds >= 0 && ds < a.D;
+        if (!planar) {
+          for (int id = lt; id < nc8 * ROWS; id += NLOADER) {
+            const int c8 = id % nc8, row = id / nc8;
+            const int r = row / SW, c = row - r * SW;
+            const int h = h0 - 1 + r, w = w0 - 1 + c;
+            const bool ok = dok && h >= 0 && h < a.H && w >= 0 && w < a.W;
+            const __nv_bfloat16* src = a.xa ? a.xa : a.xb;
+            if (ok) {
+              if (c8 < nca8) {
+                const int dd = a.upd ? ds >> 1 : ds, hh = a.up ? h >> 1 : h, ww = a.up ? w >> 1 : w;
+                src = a.xa + ((((size_t)b * Da + dd) * Ha + hh) * Wa + ww) * a.Ca + c8 * 8;
+              } else {
+                src = a.xb + ((((size_t)b * a.D + ds) * a.H + h) * a.W + w) * a.Cb + (c8 - nca8) * 8;
+              }
+            }
+            cp_async16(slab + (size_t)c8 * PLANE + row * 16, src, ok ? 16u : 0u);
+          }
+        } else {
+          // planar fp32 sources -> channels 0..nplanar-1 of the first 16-byte chunk (rest zero)
+          for (int row = lt; row < ROWS; row += NLOADER) {
+            const int r = row / SW, c = row - r * SW;
+            const int h = h0 - 1 + r, w = w0 - 1 + c;
+            const bool ok = dok && h >= 0 && h < a.H && w >= 0 && w < a.W;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (ok) {
+              const size_t off = ((size_t)ds * a.H + h) * a.W + w;
+              for (int p = 0; p < a.nplanar; ++p) v[p] = __ldg(a.xf[p] + (size_t)b * a.xf_bstride[p] + off);
+            }
+            uint4 q = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), 0u, 0u);
+            *reinterpret_cast<uint4*>(slab + row * 16) = q;
+          }
+        }
+        cp_async_commit();
+        if (prev_slot >= 0) {
+          cp_async_wait<1>();
+          fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
+          mbar_arrive(&full[prev_slot]);
+        }
+        prev_slot = slot;
+        ++cnt;
+      }
+    }
+    if (prev_slot >= 0) {
+      cp_async_wait<0>();
+      fence_proxy_async();
+      mbar_arrive(&full[prev_slot]);
+    }
+  } else if (warp == 4) {
+    // ================================ MMA ISSUER (one thread) ================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, a.NP, 0, 0);
+      const uint32_t slab_u32 = smem_u32(s_slab), w_u32 = smem_u32(s_w);
+      const uint32_t a_lbo = planar ? (smem_u32(s_zero) - slab_u32) : (uint32_t)PLANE;
+      const uint32_t b_tile = (uint32_t)a.NP * 32u;
+      mbar_wait(wbar, 0);
+      uint32_t cnt_base = 0, acc_cnt = 0;
+      for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+        const int ch = (item / HW_tiles) % a.nchunks;
+        const int d0 = ch * a.dchunk, d1 = min(d0 + a.dchunk, a.D);
+        const int nd = d1 - d0;
+        for (int j = 0; j < nd; ++j) {
+          if (a.KD == 3) {
+            if (j == 0) {
+              for (int q = 0; q < 2; ++q) { uint32_t c = cnt_base + q; mbar_wait(&full[c % NSLOT], (c / NSLOT) & 1); }
+            }
+            uint32_t c = cnt_base + j + 2;
+            mbar_wait(&full[c % NSLOT], (c / NSLOT) & 1);
+          } else {
+            uint32_t c = cnt_base + j;
+            mbar_wait(&full[c % NSLOT], (c / NSLOT) & 1);
+          }
+          const uint32_t acc = acc_cnt % NACC;
+          mbar_wait(&tempty[acc], ((acc_cnt / NACC) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * (uint32_t)a.NP;
+          uint32_t first = 1;
+          for (int kd = 0; kd < a.KD; ++kd) {
+            const uint32_t sl = (cnt_base + j + kd) % NSLOT;
+            // planar mode: LBO is relative to the start address, keep it pointing at the zero plane
+            const uint32_t slab_addr = slab_u32 + sl * slab_bytes;
+            for (int kh = 0; kh < 3; ++kh) {
+              for (int kw = 0; kw < 3; ++kw) {
+                const int tap = (kd * 3 + kh) * 3 + kw;
+                const uint32_t row_off = (uint32_t)(kh * SW + kw) * 16u;
+                for (int k = 0; k < nk16; ++k) {
+                  const uint32_t a_addr = slab_addr + (planar ? 0u : (uint32_t)(2 * k) * PLANE) + row_off;
+                  const uint32_t lbo = planar ? (a_lbo - sl * slab_bytes) : a_lbo;
+                  const uint64_t adesc = make_desc_kmajor_noswz(a_addr, lbo, (uint32_t)SW * 16u);
+                  const uint64_t bdesc = make_desc_kmajor_noswz(w_u32 + (uint32_t)(tap * nk16 + k) * b_tile, (uint32_t)a.NP * 16u, 128u);
+                  umma_f16(tmem_d, adesc, bdesc, idesc, first ? 0u : 1u);
+                  first = 0;
+                }
+              }
+            }
+          }
+          umma_commit(&tfull[acc]);
+          umma_commit(&empty[(cnt_base + j) % NSLOT]);   // oldest slab of the window is no longer needed
+          ++acc_cnt;
+        }
+        if (a.KD == 3) {
+          umma_commit(&empty[(cnt_base + nd) % NSLOT]);
+          umma_commit(&empty[(cnt_base + nd + 1) % NSLOT]);
+          cnt_base += nd + 2;
+        } else {
+          cnt_base += nd;
+        }
+      }
+    }
+  } else {
+    // ================================ EPILOGUE (warps 0-3) ================================
+    uint32_t acc_cnt = 0;
+    const int row = warp * 32 + lane;
+    const int rh = row >> 3, rw = row & 7;
+    const size_t HW = (size_t)a.H * a.W;
+    for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+      const int wt = item % a.tiles_w, ht = (item / a.tiles_w) % a.tiles_h;
+      const int ch = (item / HW_tiles) % a.nchunks, b = item / (HW_tiles * a.nchunks);
+      const int h = ht * TH + rh, w = wt * TW + rw, d0 = ch * a.dchunk, d1 = min(d0 + a.dchunk, a.D);
+      const bool inside = h < a.H && w < a.W;
+      for (int d = d0; d < d1; ++d) {
+        const uint32_t acc = acc_cnt % NACC;
+        mbar_wait(&tfull[acc], (acc_cnt / NACC) & 1);
+        tc_fence_after();
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * (uint32_t)a.NP;
+        tmem_ld16(taddr, r);
+        if (a.NP > 16) tmem_ld16(taddr + 16, r + 16);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&tempty[acc]);
+        ++acc_cnt;
+        if (!inside) continue;
+        const size_t vox = (((size_t)b * a.D + d) * a.H + h) * a.W + w;
+        if (a.out_mode == 0) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + vox * a.Cout;
+          const __nv_bfloat16* mk = a.mask ? a.mask + vox * a.Cout : nullptr;
+#pragma unroll
+          for (int c0 = 0; c0 < 32; c0 += 8) {
+            if (c0 < a.Cout) {
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float x = __uint_as_float(r[c0 + e]);
+                if (a.bias) x += __ldg(a.bias + c0 + e);
+                v[e] = x;
+              }
+              if (mk) {
+                uint4 m4 = *reinterpret_cast<const uint4*>(mk + c0);
+                const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&m4);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) if (__bfloat162float(mb[e]) < 0.f) v[e] *= a.slope;
+              } else if (a.slope >= 0.f) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = v[e] >= 0.f ? v[e] : v[e] * a.slope;
+              }
+              uint4 q = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+              *reinterpret_cast<uint4*>(o + c0) = q;
+            }
+          }
+        } else {
+          float* o = reinterpret_cast<float*>(a.out);
+          for (int c = 0; c < a.Cout; ++c) {
+            float x = __uint_as_float(r[c]);
+            if (a.bias) x += __ldg(a.bias + c);
+            if (a.slope >= 0.f) x = x >= 0.f ? x : x * a.slope;
+            o[(((size_t)b * a.Cout + c) * a.D + d) * HW + (size_t)h * a.W + w] = x;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// Weight packing: fp32 (Cout, Cin, KD, 3, 3) -> bf16 [tap][k16][2][NP][8]  (canonical K-major, no swizzle).
+// transposed == 1 packs the dgrad operator: input channels = Cout, outputs = Cin, taps flipped.
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin, int T,
+                                    int NP, int K16, int transposed) {
+  const int total = T * K16 * 2 * NP * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int e = i & 7, n = (i >> 3) % NP, kc = (i / (8 * NP)) & 1, k16 = (i / (16 * NP)) % K16, tap = i / (16 * NP * K16);
+    int ci = k16 * 16 + kc * 8 + e;
+    float v = 0.f;
+    if (!transposed) {
+      if (n < Cout && ci < Cin) v = w[((size_t)n * Cin + ci) * T + tap];
+    } else {
+      if (n < Cin && ci < Cout) v = w[((size_t)ci * Cin + n) * T + (T - 1 - tap)];
+    }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+}  // namespace tc
+}  // namespace vxm
+
+using namespace vxm;
+using namespace vxm::tc;
+
+extern "C" size_t vxm_conv3d_tc_packed_bytes(int cin_eff, int np, int kd) {
+  int k16 = (cin_eff + 15) / 16;
+  return (size_t)kd * 9 * k16 * 2 * np * 8 * sizeof(__nv_bfloat16);
+}
+
+extern "C" int vxm_conv3d_tc_pack(const float* w, void* wpk, int Cout, int Cin, int kd, int np, int transposed, void* stream) {
+  VXM_REQUIRE(w && wpk && Cout > 0 && Cin > 0 && (kd == 1 || kd == 3) && np % 16 == 0 && np <= 32, "conv3d_tc_pack: bad argument");
+  int cin_eff = transposed ? Cout : Cin, nout = transposed ? Cin : Cout;
+  VXM_REQUIRE(nout <= np, "conv3d_tc_pack: %d output channels do not fit N=%d", nout, np);
+  int K16 = (cin_eff + 15) / 16, T = kd * 9;
+  int total = T * K16 * 2 * np * 8;
+  pack_weights_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(w, (__nv_bfloat16*)wpk, Cout, Cin, T, np, K16, transposed);
+  return check_launch("conv3d_tc_pack");
+}
+
+extern "C" int vxm_conv3d_tc_fwd(const void* xa, const void* xb, const float* const* xf, const long long* xf_bstride, int nplanar,
+                                 const void* wpk, const float* bias, void* out, const void* mask, int B, int D, int H, int W,
+                                 int Ca, int Cb, int up, int Cout, int np, int kd, int out_mode, float slope, void* stream) {
+  VXM_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && wpk && out, "conv3d_tc_fwd: bad argument");
+  VXM_REQUIRE(kd == 1 || kd == 3, "conv3d_tc_fwd: kd must be 1 or 3");
+  VXM_REQUIRE(np == 16 || np == 32, "conv3d_tc_fwd: N must be 16 or 32");
+  VXM_REQUIRE(Cout > 0 && Cout <= np && (out_mode == 1 || Cout % 8 == 0), "conv3d_tc_fwd: unsupported Cout %d", Cout);
+  ConvTcArgs a{};
+  int Cin;
+  if (nplanar > 0) {
+    VXM_REQUIRE(nplanar <= 4 && xf && xf_bstride, "conv3d_tc_fwd: at most 4 planar fp32 sources");
+    for (int i = 0; i < nplanar; ++i) { a.xf[i] = xf[i]; a.xf_bstride[i] = xf_bstride[i]; }
+    a.nplanar = nplanar;
+    Cin = 16;
+  } else {
+    VXM_REQUIRE(xa || xb, "conv3d_tc_fwd: no input");
+    VXM_REQUIRE(Ca % 8 == 0 && Cb % 8 == 0 && (Ca + Cb) % 16 == 0 && Ca + Cb >= 16 && Ca + Cb <= 64,
+                "conv3d_tc_fwd: channel counts (%d,%d) unsupported", Ca, Cb);
+    VXM_REQUIRE((Ca == 0 || xa) && (Cb == 0 || xb), "conv3d_tc_fwd: missing source tensor");
+    VXM_REQUIRE(!up || (H % 2 == 0 && W % 2 == 0 && (kd == 1 || D % 2 == 0)), "conv3d_tc_fwd: upsampled source needs even sizes");
+    Cin = Ca + Cb;
+  }
+  a.xa = (const __nv_bfloat16*)xa; a.xb = (const __nv_bfloat16*)xb; a.wpk = (const __nv_bfloat16*)wpk; a.bias = bias;
+  a.out = out; a.mask = (const __nv_bfloat16*)mask;
+  a.B = B; a.D = D; a.H = H; a.W = W; a.Ca = Ca; a.Cb = Cb; a.up = up; a.upd = (up && kd == 3) ? 1 : 0;
+  a.Cout = Cout; a.NP = np; a.KD = kd; a.out_mode = out_mode; a.slope = slope;
+  a.tiles_h = (H + TH - 1) / TH; a.tiles_w = (W + TW - 1) / TW;
+  int nsm = sm_count();
+  int dchunk = D;
+  auto items = [&](int dc) { return (long long)B * a.tiles_h * a.tiles_w * ((D + dc - 1) / dc); };
+  while (items(dchunk) < 4LL * nsm && dchunk > 8) dchunk = (dchunk + 1) / 2;
+  a.dchunk = dchunk; a.nchunks = (D + dchunk - 1) / dchunk;
+  long long ni = items(dchunk);
+  VXM_REQUIRE(ni < (1LL << 31), "conv3d_tc_fwd: too many tiles");
+  a.nitems = (int)ni;
+  a.wbytes = (uint32_t)vxm_conv3d_tc_packed_bytes(Cin, np, kd);
+  int nc8 = nplanar > 0 ? 1 : Cin / 8;
+  size_t smem = ((a.wbytes + 127u) & ~127u) + (size_t)NSLOT * nc8 * PLANE + PLANE + 256;
+  VXM_REQUIRE(smem <= 227 * 1024, "conv3d_tc_fwd: %zu bytes of shared memory needed", smem);
+  VXM_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = a.nitems < nsm ? a.nitems : nsm;
+  conv_tc_kernel<<<grid, NTHREADS, smem, as_stream(stream)>>>(a);
+  return check_launch("conv3d_tc_fwd");
+}

@@ -1,0 +1,77 @@
+"""Host wrappers of the tcgen05 implicit-GEMM convolution engine (csrc/conv3d_tc.cu, csrc/conv3d_tc_wgrad.cu).
+
+Activations of this engine are bf16, channels-last: a (B, C, D, H, W) logical tensor is held as a contiguous
+(B, D, H, W, C) bf16 tensor (`ndhwc`).  Weights stay fp32 in the nn.Module (reference layout
+(Cout, Cin, 3, 3, 3)); packed bf16 copies are refreshed whenever the parameter version changes.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def np_for(cout):
+    """MMA N (16 or 32) for a layer with `cout` output channels."""
+    if cout <= 16:
+        return 16
+    if cout <= 32:
+        return 32
+    raise _lib.VxmError("tcgen05 conv engine: at most 32 output channels per layer (got %d)" % cout)
+
+
+def to_ndhwc_bf16(x):
+    """(B,C,D,H,W) fp32 -> (B,D,H,W,C) bf16 contiguous (test / boundary helper; torch copy kernels)."""
+    return x.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16)
+
+
+def from_ndhwc(x):
+    return x.permute(0, 4, 1, 2, 3).float().contiguous()
+
+
+def pack_weights(w, transposed=False):
+    """fp32 (Cout, Cin, kd, 3, 3) -> packed bf16 operand for vxm_conv3d_tc_fwd (dgrad operator if transposed)."""
+    lib = _lib.load()
+    if w.dim() == 4:
+        w = w.unsqueeze(2)
+    w = w.contiguous()
+    Cout, Cin, kd = w.shape[0], w.shape[1], w.shape[2]
+    cin_eff, nout = (Cout, Cin) if transposed else (Cin, Cout)
+    NP = np_for(nout)
+    nbytes = int(lib.vxm_conv3d_tc_packed_bytes(cin_eff, NP, kd))
+    out = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
+    _lib.check(lib.vxm_conv3d_tc_pack(_lib.ptr(w), _lib.ptr(out), Cout, Cin, kd, NP, 1 if transposed else 0,
+                                      _lib.stream_ptr()), "vxm_conv3d_tc_pack")
+    return out, NP
+
+
+def conv_fwd(xa, xb, wpk, NP, bias, cout, kd, up=False, planar=None, out_fp32_planar=False, slope=None, mask=None):
+    """Launch the tensor-core convolution.  xa / xb: bf16 NDHWC tensors (xa at half resolution when `up`);
+    planar: list of <= 4 fp32 (B,1,D,H,W) tensors used instead of xa/xb.  Returns bf16 NDHWC (B,D,H,W,cout)
+    or, with out_fp32_planar, fp32 (B,cout,D,H,W)."""
+    lib = _lib.load()
+    if planar is not None:
+        ref = planar[0]
+        B, D, H, W = ref.shape[0], ref.shape[-3] if ref.dim() == 5 else 1, ref.shape[-2], ref.shape[-1]
+        arr_p = (ctypes.c_void_p * 4)(*([p.data_ptr() for p in planar] + [0] * (4 - len(planar))))
+        arr_s = (ctypes.c_longlong * 4)(*([p.stride(0) for p in planar] + [0] * (4 - len(planar))))
+        xf, xs, npl, Ca, Cb = arr_p, arr_s, len(planar), 0, 0
+        dev = ref.device
+    else:
+        full = xb if xb is not None else xa
+        B, D, H, W = full.shape[0], full.shape[1], full.shape[2], full.shape[3]
+        if xb is None and up:
+            D, H, W = (D * 2 if kd == 3 else D), H * 2, W * 2
+        Ca = 0 if xa is None else xa.shape[-1]
+        Cb = 0 if xb is None else xb.shape[-1]
+        xf, xs, npl = None, None, 0
+        dev = full.device
+    if out_fp32_planar:
+        out = torch.empty((B, cout, D, H, W), dtype=torch.float32, device=dev)
+    else:
+        out = torch.empty((B, D, H, W, cout), dtype=torch.bfloat16, device=dev)
+    s = -1.0 if slope is None else float(slope)
+    _lib.check(lib.vxm_conv3d_tc_fwd(_lib.ptr(xa), _lib.ptr(xb), xf, xs, npl, _lib.ptr(wpk), _lib.ptr(bias), _lib.ptr(out),
+                                     _lib.ptr(mask), B, D, H, W, Ca, Cb, 1 if up else 0, cout, NP, kd,
+                                     1 if out_fp32_planar else 0, s, _lib.stream_ptr()), "vxm_conv3d_tc_fwd")
+    return out
