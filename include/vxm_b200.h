@@ -154,6 +154,16 @@ int vxm_conv3d_tc_fwd(const void* xa, const void* xb, const float* const* xf, co
                       int nplanar, const void* wpk, const float* bias, void* out, const void* mask,
                       int B, int D, int H, int W, int Ca, int Cb, int up, int Cout, int np, int kd,
                       int out_mode, float slope, void* stream);
+/* Weight (and bias) gradient on tensor cores.  x sources as in vxm_conv3d_tc_fwd (the layer's forward input);
+ * gz = gradient w.r.t. the convolution output (already multiplied by the activation derivative): bf16 NDHWC with
+ * Cg in {8,16,32} channels, or nplanar_g (<= 4) planar fp32 volumes (flow head).  grad_w: fp32
+ * (Cout_real, Cin_real, kd, 3, 3), overwritten; grad_b: fp32 (Cout_real), overwritten, may be NULL (and must be
+ * NULL for planar gz).  work: vxm_conv3d_tc_wgrad_workspace_bytes(kd). */
+size_t vxm_conv3d_tc_wgrad_workspace_bytes(int kd);
+int vxm_conv3d_tc_wgrad(const void* xa, const void* xb, const float* const* xf, const long long* xf_bstride,
+                        int nplanar_x, const void* gz, const float* const* gf, const long long* gf_bstride,
+                        int nplanar_g, float* grad_w, float* grad_b, void* work, int B, int D, int H, int W,
+                        int Ca, int Cb, int up, int Cin_real, int Cg, int Cout_real, int kd, void* stream);
 
 /* ---- MaxPool(2) / nearest Upsample(2) + concat: reference networks.py:83-85,130,137-138 ----
  * pool factor is 2 on H, W and on D when D > 1 (nd == 3).  idx (uint8, same shape as y) stores the

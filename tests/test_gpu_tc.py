@@ -99,3 +99,59 @@ def test_tc_dgrad_with_mask(tc, cuda):
     out = tc.conv_fwd(tc.to_ndhwc_bf16(gy.to(cuda)), None, wpk, NP, None, Cin, 3, slope=0.2,
                       mask=tc.to_ndhwc_bf16(below.to(cuda)))
     assert rel_err(tc.from_ndhwc(out).cpu(), ref) <= 1e-2
+
+
+WG_CASES = [
+    # shape, Ca, Cb, up, Cout
+    ((4, 16, 8), 16, 0, False, 16),
+    ((12, 24, 20), 32, 0, False, 32),
+    ((10, 12, 14), 32, 0, False, 32),
+    ((8, 32, 16), 32, 16, True, 32),
+    ((8, 16, 16), 32, 32, True, 32),
+    ((6, 16, 24), 32, 0, False, 16),
+    ((1, 32, 24), 16, 0, False, 32),
+]
+
+
+@pytest.mark.parametrize("shape,Ca,Cb,up,Cout", WG_CASES)
+def test_tc_wgrad(tc, cuda, shape, Ca, Cb, up, Cout):
+    g = torch.Generator().manual_seed(11)
+    kd = 1 if shape[0] == 1 else 3
+    D, H, W = shape
+    ashape = ((D // 2 if kd == 3 else D), H // 2, W // 2) if up else shape
+    xa = bf(torch.randn((2, Ca) + ashape, generator=g))
+    xb = bf(torch.randn((2, Cb) + shape, generator=g)) if Cb else None
+    gz = bf(torch.randn((2, Cout) + shape, generator=g))
+    xin = xa
+    if up:
+        xin = F.interpolate(xa, scale_factor=(2 if kd == 3 else 1, 2, 2), mode="nearest")
+    if xb is not None:
+        xin = torch.cat([xin, xb], dim=1)
+    w = torch.zeros((Cout, Ca + Cb, kd, 3, 3), dtype=torch.float64, requires_grad=True)
+    b = torch.zeros(Cout, dtype=torch.float64, requires_grad=True)
+    F.conv3d(xin.double(), w, b, padding=(kd // 2, 1, 1)).backward(gz.double())
+    gw, gb = tc.conv_wgrad(tc.to_ndhwc_bf16(xa.to(cuda)), None if xb is None else tc.to_ndhwc_bf16(xb.to(cuda)),
+                           tc.to_ndhwc_bf16(gz.to(cuda)), Ca + Cb, Cout, kd, up=up)
+    assert rel_err(gw.cpu(), w.grad) <= 1e-4
+    assert rel_err(gb.cpu(), b.grad) <= 1e-4
+
+
+def test_tc_wgrad_planar_sources(tc, cuda):
+    g = torch.Generator().manual_seed(12)
+    shape = (8, 24, 16)
+    src, trg = torch.rand((2, 1) + shape, generator=g), torch.rand((2, 1) + shape, generator=g)
+    gz = bf(torch.randn((2, 16) + shape, generator=g))
+    w = torch.zeros((16, 2, 3, 3, 3), dtype=torch.float64, requires_grad=True)
+    F.conv3d(bf(torch.cat([src, trg], 1)).double(), w, None, padding=1).backward(gz.double())
+    gw, _ = tc.conv_wgrad(None, None, tc.to_ndhwc_bf16(gz.to(cuda)), 2, 16, 3, planar_x=[src.to(cuda), trg.to(cuda)])
+    assert rel_err(gw.cpu(), w.grad) <= 1e-4
+    # flow head: planar fp32 gz (3 channels), bf16 x
+    x = bf(torch.randn((2, 16) + shape, generator=g))
+    gfl = torch.randn((2, 3) + shape, generator=g)
+    w = torch.zeros((3, 16, 3, 3, 3), dtype=torch.float64, requires_grad=True)
+    F.conv3d(x.double(), w, None, padding=1).backward(bf(gfl).double())
+    planes = [gfl[:, i:i + 1].to(cuda) for i in range(3)]
+    gfl_dev = gfl.to(cuda)
+    planes = [gfl_dev[:, i:i + 1] for i in range(3)]
+    gw, _ = tc.conv_wgrad(tc.to_ndhwc_bf16(x.to(cuda)), None, None, 16, 3, 3, planar_g=planes)
+    assert rel_err(gw.cpu(), w.grad) <= 1e-4

@@ -19,6 +19,8 @@
 //     issues tcgen05.mma and tcgen05.commit; warps 0-3 drain TMEM (tcgen05.ld: one voxel's Cout channels per
 //     thread), add bias, apply LeakyReLU (or the dgrad mask) and write 16-byte bf16 NDHWC vectors.
 //     Pipelines: slab ring full/empty mbarriers (loader <-> MMA), TMEM full/empty (MMA <-> epilogue).
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace vxm {
@@ -28,7 +30,7 @@ constexpr int TH = 16, TW = 8;
 constexpr int SW = TW + 2, SH = TH + 2;
 constexpr int ROWS = SH * SW;     // 180 voxels per channel-chunk plane
 constexpr int PLANE = ROWS * 16;  // bytes
-constexpr int NSLOT = 4, NACC = 2;
+constexpr int MAXSLOT = 8, NACC = 2, KMAX = 12;
 constexpr int NLOADER = 128, NTHREADS = 288;
 
 struct ConvTcArgs {
@@ -45,30 +47,32 @@ struct ConvTcArgs {
   int Ca, Cb, up, upd;
   int Cout, NP, KD, out_mode;
   float slope;
-  int tiles_h, tiles_w, dchunk, nchunks, nitems;
+  int tiles_h, tiles_w, dchunk, nchunks, nitems, nslot;
   uint32_t wbytes;
 };
 
+template <int KD, int NK16, int NP>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const ConvTcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const bool planar = a.nplanar > 0;
-  const int Cin = planar ? 16 : a.Ca + a.Cb;
-  const int nk16 = Cin / 16;
+  const int Cin = NK16 * 16;
+  constexpr int nk16 = NK16;
   const int nc8 = planar ? 1 : Cin / 8;            // staged planes (planar mode: plane 0 data + a shared zero plane)
   const uint32_t slab_bytes = (uint32_t)nc8 * PLANE;
   uint8_t* s_w = smem;
   uint8_t* s_slab = smem + ((a.wbytes + 127u) & ~127u);
+  const int NSLOT = a.nslot;
   uint8_t* s_zero = s_slab + NSLOT * slab_bytes;   // one all-zero plane (only used in planar mode)
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_zero + PLANE);
   uint64_t* full = bars;
-  uint64_t* empty = bars + NSLOT;
-  uint64_t* tfull = bars + 2 * NSLOT;
+  uint64_t* empty = bars + MAXSLOT;
+  uint64_t* tfull = bars + 2 * MAXSLOT;
   uint64_t* tempty = tfull + NACC;
   uint64_t* wbar = tempty + NACC;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tmem_cols = (NACC * a.NP <= 32) ? 32u : ((NACC * a.NP <= 64) ? 64u : 128u);
+  constexpr uint32_t tmem_cols = (NACC * NP <= 32) ? 32u : ((NACC * NP <= 64) ? 64u : 128u);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSLOT; ++i) { mbar_init(&full[i], NLOADER); mbar_init(&empty[i], 1); }
@@ -96,38 +100,57 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const ConvTcArgs a
 
   if (warp >= 5) {
     // ================================ LOADER (128 threads) ================================
+    // Runs ahead of the tensor core by (nslot - 3) slabs.  cp.async completion is reported straight to the
+    // slab's "full" mbarrier (cp.async.mbarrier.arrive.noinc), so issuing slab s+1 never waits for slab s.
     const int lt = threadIdx.x - 5 * 32;
     uint32_t cnt = 0;
-    int prev_slot = -1;
     const int Da = a.upd ? a.D >> 1 : a.D, Ha = a.up ? a.H >> 1 : a.H, Wa = a.up ? a.W >> 1 : a.W;
     const int nca8 = a.Ca >> 3;
+    const int nchunk = nc8 * ROWS;
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
       const int wt = item % a.tiles_w, ht = (item / a.tiles_w) % a.tiles_h;
       const int ch = (item / HW_tiles) % a.nchunks, b = item / (HW_tiles * a.nchunks);
       const int h0 = ht * TH, w0 = wt * TW, d0 = ch * a.dchunk, d1 = min(d0 + a.dchunk, a.D);
-      const int s_begin = a.KD == 3 ? d0 - 1 : d0, s_end = a.KD == 3 ? d1 + 1 : d1;
+      const int s_begin = KD == 3 ? d0 - 1 : d0, s_end = KD == 3 ? d1 + 1 : d1;
+      // per-item address table of this thread's 16-byte chunks: (source offset within a slice | source select), smem offset
+      int soff[KMAX];
+      uint32_t doff[KMAX];
+      if (!planar) {
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          const int id = lt + k * NLOADER;
+          soff[k] = -1;
+          doff[k] = 0;
+          if (id < nchunk) {
+            const int c8 = id % nc8, row = id / nc8;
+            const int r = row / SW, c = row - r * SW;
+            const int h = h0 - 1 + r, w = w0 - 1 + c;
+            doff[k] = (uint32_t)c8 * PLANE + (uint32_t)row * 16u;
+            if (h >= 0 && h < a.H && w >= 0 && w < a.W) {
+              if (c8 < nca8) soff[k] = (((a.up ? h >> 1 : h) * Wa + (a.up ? w >> 1 : w)) * a.Ca + c8 * 8) << 1;
+              else soff[k] = (((h * a.W + w) * a.Cb + (c8 - nca8) * 8) << 1) | 1;
+            }
+          }
+        }
+      }
       for (int ds = s_begin; ds < s_end; ++ds) {
         const int slot = cnt % NSLOT;
         mbar_wait(&empty[slot], ((cnt / NSLOT) & 1) ^ 1);
         uint8_t* slab = s_slab + (size_t)slot * slab_bytes;
         const bool dok = ds >= 0 && ds < a.D;
         if (!planar) {
-          for (int id = lt; id < nc8 * ROWS; id += NLOADER) {
-            const int c8 = id % nc8, row = id / nc8;
-            const int r = row / SW, c = row - r * SW;
-            const int h = h0 - 1 + r, w = w0 - 1 + c;
-            const bool ok = dok && h >= 0 && h < a.H && w >= 0 && w < a.W;
-            const __nv_bfloat16* src = a.xa ? a.xa : a.xb;
-            if (ok) {
-              if (c8 < nca8) {
-                const int dd = a.upd ? ds >> 1 : ds, hh = a.up ? h >> 1 : h, ww = a.up ? w >> 1 : w;
-                src = a.xa + ((((size_t)b * Da + dd) * Ha + hh) * Wa + ww) * a.Ca + c8 * 8;
-              } else {
-                src = a.xb + ((((size_t)b * a.D + ds) * a.H + h) * a.W + w) * a.Cb + (c8 - nca8) * 8;
-              }
+          const __nv_bfloat16* baseA = a.xa ? a.xa + (((size_t)b * Da + (dok ? (a.upd ? ds >> 1 : ds) : 0)) * Ha * Wa) * a.Ca : nullptr;
+          const __nv_bfloat16* baseB = a.xb ? a.xb + (((size_t)b * a.D + (dok ? ds : 0)) * a.H * a.W) * a.Cb : nullptr;
+          const __nv_bfloat16* dummy = a.xa ? a.xa : a.xb;
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k) {
+            if (lt + k * NLOADER < nchunk) {
+              const bool ok = dok && soff[k] >= 0;
+              const __nv_bfloat16* src = ok ? ((soff[k] & 1) ? baseB : baseA) + (soff[k] >> 1) : dummy;
+              cp_async16(slab + doff[k], src, ok ? 16u : 0u);
             }
-            cp_async16(slab + (size_t)c8 * PLANE + row * 16, src, ok ? 16u : 0u);
           }
+          cp_async_arrive_noinc(&full[slot]);
         } else {
           // planar fp32 sources -> channels 0..nplanar-1 of the first 16-byte chunk (rest zero)
           for (int row = lt; row < ROWS; row += NLOADER) {
@@ -142,37 +165,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const ConvTcArgs a
             uint4 q = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), 0u, 0u);
             *reinterpret_cast<uint4*>(slab + row * 16) = q;
           }
+          fence_proxy_async();   // generic-proxy stores -> visible to the tensor core (async proxy)
+          mbar_arrive(&full[slot]);
         }
-        cp_async_commit();
-        if (prev_slot >= 0) {
-          cp_async_wait<1>();
-          fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
-          mbar_arrive(&full[prev_slot]);
-        }
-        prev_slot = slot;
         ++cnt;
       }
     }
-    if (prev_slot >= 0) {
-      cp_async_wait<0>();
-      fence_proxy_async();
-      mbar_arrive(&full[prev_slot]);
-    }
   } else if (warp == 4) {
     // ================================ MMA ISSUER (one thread) ================================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, a.NP, 0, 0);
+    // The whole warp runs this loop (warp-uniform control flow keeps the descriptors in uniform registers);
+    // one elected lane issues the tcgen05 instructions.
+    {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t slab_u32 = smem_u32(s_slab), w_u32 = smem_u32(s_w);
       const uint32_t a_lbo = planar ? (smem_u32(s_zero) - slab_u32) : (uint32_t)PLANE;
-      const uint32_t b_tile = (uint32_t)a.NP * 32u;
+      constexpr uint32_t b_tile16 = (uint32_t)NP * 32u / 16u;
       mbar_wait(wbar, 0);
+      const uint64_t bdesc0 = make_desc_kmajor_noswz(w_u32, (uint32_t)NP * 16u, 128u);
       uint32_t cnt_base = 0, acc_cnt = 0;
       for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
         const int ch = (item / HW_tiles) % a.nchunks;
         const int d0 = ch * a.dchunk, d1 = min(d0 + a.dchunk, a.D);
         const int nd = d1 - d0;
         for (int j = 0; j < nd; ++j) {
-          if (a.KD == 3) {
+          if (KD == 3) {
             if (j == 0) {
               for (int q = 0; q < 2; ++q) { uint32_t c = cnt_base + q; mbar_wait(&full[c % NSLOT], (c / NSLOT) & 1); }
             }
@@ -185,34 +201,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const ConvTcArgs a
           const uint32_t acc = acc_cnt % NACC;
           mbar_wait(&tempty[acc], ((acc_cnt / NACC) & 1) ^ 1);
           tc_fence_after();
-          const uint32_t tmem_d = tmem_base + acc * (uint32_t)a.NP;
-          uint32_t first = 1;
-          for (int kd = 0; kd < a.KD; ++kd) {
+          const uint32_t tmem_d = tmem_base + acc * (uint32_t)NP;
+          uint64_t adesc_kd[KD];
+#pragma unroll
+          for (int kd = 0; kd < KD; ++kd) {
             const uint32_t sl = (cnt_base + j + kd) % NSLOT;
-            // planar mode: LBO is relative to the start address, keep it pointing at the zero plane
-            const uint32_t slab_addr = slab_u32 + sl * slab_bytes;
-            for (int kh = 0; kh < 3; ++kh) {
-              for (int kw = 0; kw < 3; ++kw) {
-                const int tap = (kd * 3 + kh) * 3 + kw;
-                const uint32_t row_off = (uint32_t)(kh * SW + kw) * 16u;
-                for (int k = 0; k < nk16; ++k) {
-                  const uint32_t a_addr = slab_addr + (planar ? 0u : (uint32_t)(2 * k) * PLANE) + row_off;
-                  const uint32_t lbo = planar ? (a_lbo - sl * slab_bytes) : a_lbo;
-                  const uint64_t adesc = make_desc_kmajor_noswz(a_addr, lbo, (uint32_t)SW * 16u);
-                  const uint64_t bdesc = make_desc_kmajor_noswz(w_u32 + (uint32_t)(tap * nk16 + k) * b_tile, (uint32_t)a.NP * 16u, 128u);
-                  umma_f16(tmem_d, adesc, bdesc, idesc, first ? 0u : 1u);
-                  first = 0;
+            // planar mode: the second K chunk (channels 8..15) reads the shared all-zero plane
+            adesc_kd[kd] = make_desc_kmajor_noswz(slab_u32 + sl * slab_bytes, planar ? (a_lbo - sl * slab_bytes) : a_lbo, (uint32_t)SW * 16u);
+          }
+          if (elect_one()) {
+#pragma unroll
+            for (int kd = 0; kd < KD; ++kd) {
+#pragma unroll
+              for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+                  for (int k = 0; k < NK16; ++k) {
+                    constexpr int dummy = 0; (void)dummy;
+                    const int tap = (kd * 3 + kh) * 3 + kw;
+                    // start-address field is in 16-byte units: tap shift (kh*SW + kw) rows, K step = 2 planes
+                    const uint64_t adesc = adesc_kd[kd] + (uint64_t)(kh * SW + kw + k * (2 * PLANE / 16));
+                    const uint64_t bdesc = bdesc0 + (uint64_t)((tap * NK16 + k) * b_tile16);
+                    umma_f16(tmem_d, adesc, bdesc, idesc, (kd | kh | kw | k) ? 1u : 0u);
+                  }
                 }
               }
             }
+            umma_commit(&tfull[acc]);
+            umma_commit(&empty[(cnt_base + j) % NSLOT]);   // oldest slab of the window is no longer needed
           }
-          umma_commit(&tfull[acc]);
-          umma_commit(&empty[(cnt_base + j) % NSLOT]);   // oldest slab of the window is no longer needed
+          __syncwarp();
           ++acc_cnt;
         }
-        if (a.KD == 3) {
-          umma_commit(&empty[(cnt_base + nd) % NSLOT]);
-          umma_commit(&empty[(cnt_base + nd + 1) % NSLOT]);
+        if (KD == 3) {
+          if (elect_one()) {
+            umma_commit(&empty[(cnt_base + nd) % NSLOT]);
+            umma_commit(&empty[(cnt_base + nd + 1) % NSLOT]);
+          }
+          __syncwarp();
           cnt_base += nd + 2;
         } else {
           cnt_base += nd;
@@ -234,10 +261,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const ConvTcArgs a
         const uint32_t acc = acc_cnt % NACC;
         mbar_wait(&tfull[acc], (acc_cnt / NACC) & 1);
         tc_fence_after();
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * (uint32_t)a.NP;
+        uint32_t r[NP];
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * (uint32_t)NP;
         tmem_ld16(taddr, r);
-        if (a.NP > 16) tmem_ld16(taddr + 16, r + 16);
+        if constexpr (NP > 16) tmem_ld16(taddr + 16, r + 16);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&tempty[acc]);
@@ -248,7 +275,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const ConvTcArgs a
           __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + vox * a.Cout;
           const __nv_bfloat16* mk = a.mask ? a.mask + vox * a.Cout : nullptr;
 #pragma unroll
-          for (int c0 = 0; c0 < 32; c0 += 8) {
+          for (int c0 = 0; c0 < NP; c0 += 8) {
             if (c0 < a.Cout) {
               float v[8];
 #pragma unroll
@@ -272,11 +299,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const ConvTcArgs a
           }
         } else {
           float* o = reinterpret_cast<float*>(a.out);
-          for (int c = 0; c < a.Cout; ++c) {
-            float x = __uint_as_float(r[c]);
-            if (a.bias) x += __ldg(a.bias + c);
-            if (a.slope >= 0.f) x = x >= 0.f ? x : x * a.slope;
-            o[(((size_t)b * a.Cout + c) * a.D + d) * HW + (size_t)h * a.W + w] = x;
+#pragma unroll
+          for (int c = 0; c < NP; ++c) {
+            if (c < a.Cout) {
+              float x = __uint_as_float(r[c]);
+              if (a.bias) x += __ldg(a.bias + c);
+              if (a.slope >= 0.f) x = x >= 0.f ? x : x * a.slope;
+              o[(((size_t)b * a.Cout + c) * a.D + d) * HW + (size_t)h * a.W + w] = x;
+            }
           }
         }
       }
@@ -363,10 +393,29 @@ extern "C" int vxm_conv3d_tc_fwd(const void* xa, const void* xb, const float* co
   a.nitems = (int)ni;
   a.wbytes = (uint32_t)vxm_conv3d_tc_packed_bytes(Cin, np, kd);
   int nc8 = nplanar > 0 ? 1 : Cin / 8;
-  size_t smem = ((a.wbytes + 127u) & ~127u) + (size_t)NSLOT * nc8 * PLANE + PLANE + 256;
-  VXM_REQUIRE(smem <= 227 * 1024, "conv3d_tc_fwd: %zu bytes of shared memory needed", smem);
-  VXM_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VXM_REQUIRE(nc8 * ROWS <= KMAX * NLOADER, "conv3d_tc_fwd: slab too large for the loader table");
+  size_t fixed = ((a.wbytes + 127u) & ~127u) + PLANE + 256;
+  int nslot = (int)((227 * 1024 - fixed) / ((size_t)nc8 * PLANE));
+  if (nslot > MAXSLOT) nslot = MAXSLOT;
+  VXM_REQUIRE(nslot >= 4, "conv3d_tc_fwd: not enough shared memory for the slab ring");
+  a.nslot = nslot;
+  size_t smem = fixed + (size_t)nslot * nc8 * PLANE;
   int grid = a.nitems < nsm ? a.nitems : nsm;
-  conv_tc_kernel<<<grid, NTHREADS, smem, as_stream(stream)>>>(a);
+  int nk16 = Cin / 16;
+  cudaStream_t st = as_stream(stream);
+#define VXM_TC_LAUNCH(KD_, NK_, NP_)                                                                                   \
+  do {                                                                                                                 \
+    VXM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KD_, NK_, NP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    conv_tc_kernel<KD_, NK_, NP_><<<grid, NTHREADS, smem, st>>>(a);                                                     \
+  } while (0)
+#define VXM_TC_NK(KD_, NP_)                                                    \
+  switch (nk16) {                                                              \
+    case 1: VXM_TC_LAUNCH(KD_, 1, NP_); break;                                 \
+    case 2: VXM_TC_LAUNCH(KD_, 2, NP_); break;                                 \
+    case 3: VXM_TC_LAUNCH(KD_, 3, NP_); break;                                 \
+    default: VXM_TC_LAUNCH(KD_, 4, NP_); break;                                \
+  }
+  if (kd == 3) { if (np == 16) { VXM_TC_NK(3, 16) } else { VXM_TC_NK(3, 32) } }
+  else { if (np == 16) { VXM_TC_NK(1, 16) } else { VXM_TC_NK(1, 32) } }
   return check_launch("conv3d_tc_fwd");
 }

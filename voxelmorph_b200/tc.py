@@ -75,3 +75,40 @@ def conv_fwd(xa, xb, wpk, NP, bias, cout, kd, up=False, planar=None, out_fp32_pl
                                      _lib.ptr(mask), B, D, H, W, Ca, Cb, 1 if up else 0, cout, NP, kd,
                                      1 if out_fp32_planar else 0, s, _lib.stream_ptr()), "vxm_conv3d_tc_fwd")
     return out
+
+
+def _planar_args(planar):
+    if planar is None:
+        return None, None, 0
+    arr_p = (ctypes.c_void_p * 4)(*([p.data_ptr() for p in planar] + [0] * (4 - len(planar))))
+    arr_s = (ctypes.c_longlong * 4)(*([p.stride(0) for p in planar] + [0] * (4 - len(planar))))
+    return arr_p, arr_s, len(planar)
+
+
+_wgrad_ws = {}
+
+
+def conv_wgrad(xa, xb, gz, cin, cout, kd, up=False, planar_x=None, planar_g=None, need_bias=True):
+    """fp32 grad_w (cout, cin, kd, 3, 3) and grad_b (cout) from the layer input (xa/xb or planar_x) and gz."""
+    lib = _lib.load()
+    ref = gz if gz is not None else planar_g[0]
+    dev = ref.device
+    if gz is not None:
+        B, D, H, W, Cg = gz.shape
+    else:
+        B, D, H, W, Cg = ref.shape[0], (ref.shape[-3] if ref.dim() == 5 else 1), ref.shape[-2], ref.shape[-1], 8
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream, kd)
+    work = _wgrad_ws.get(key)
+    if work is None:
+        work = torch.empty(int(lib.vxm_conv3d_tc_wgrad_workspace_bytes(kd)), dtype=torch.uint8, device=dev)
+        _wgrad_ws[key] = work
+    gw = torch.empty((cout, cin, kd, 3, 3), dtype=torch.float32, device=dev)
+    gb = torch.empty(cout, dtype=torch.float32, device=dev) if (need_bias and planar_g is None) else None
+    xf, xs, npx = _planar_args(planar_x)
+    gf, gs, npg = _planar_args(planar_g)
+    Ca = 0 if xa is None else xa.shape[-1]
+    Cb = 0 if xb is None else xb.shape[-1]
+    _lib.check(lib.vxm_conv3d_tc_wgrad(_lib.ptr(xa), _lib.ptr(xb), xf, xs, npx, _lib.ptr(gz), gf, gs, npg, _lib.ptr(gw),
+                                       _lib.ptr(gb), _lib.ptr(work), B, D, H, W, Ca, Cb, 1 if up else 0, cin, Cg, cout, kd,
+                                       _lib.stream_ptr()), "vxm_conv3d_tc_wgrad")
+    return gw, gb
