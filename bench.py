@@ -31,6 +31,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--shape", type=int, nargs=3, default=list(FULL), help="debug only; the metric is quoted at 160 192 224")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--engine", default=None, choices=["f32", "bf16"], help="convolution engine (default: bf16 tensor-core engine)")
     ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline legs")
     return ap.parse_args()
 
@@ -199,6 +200,7 @@ def b200_arm(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     vxm._lib.load()
+    os.environ["VXM_B200_CONV_ENGINE"] = args.engine or os.environ.get("VXM_B200_CONV_ENGINE", "bf16")
     peaks = load_peaks()
     shape = tuple(args.shape)
     V = int(np.prod(shape))
@@ -320,18 +322,24 @@ def b200_arm(args):
             return r
         return inner
 
-    ops._ConvK3Fn.forward = staticmethod(timed(orig_fwd))
-    ops._ConvK3Fn.backward = staticmethod(timed(orig_bwd))
+    from voxelmorph_b200 import tc as tcmod
+    o_cf, o_cw = tcmod.conv_fwd, tcmod.conv_wgrad
+    if ops.conv_engine() == "bf16":
+        tcmod.conv_fwd, tcmod.conv_wgrad = timed(o_cf), timed(o_cw)
+    else:
+        ops._ConvK3Fn.forward = staticmethod(timed(orig_fwd))
+        ops._ConvK3Fn.backward = staticmethod(timed(orig_bwd))
     NPROF = 2
     for i in range(NPROF):
         step(*pairs_dev[i % NPAIR])
     torch.cuda.synchronize()
     ops._ConvK3Fn.forward, ops._ConvK3Fn.backward = staticmethod(orig_fwd), staticmethod(orig_bwd)
+    tcmod.conv_fwd, tcmod.conv_wgrad = o_cf, o_cw
     conv_total_ms = sum(a.elapsed_time(b) for a, b in conv_ms) / NPROF
     _, flops_step = conv_flops_per_step(shape)
     ach = flops_step / (conv_total_ms * 1e-3) / 1e12
     engine = ops.conv_engine()
-    roofline = dict(bound="tensor", kernel="conv3d k3 fwd+dgrad+wgrad, all 12 layers (%s engine)" % engine,
+    roofline = dict(bound="tensor", kernel="conv3d k3 fwd+dgrad+wgrad, all 12 layers (%s)" % ("tcgen05 bf16 implicit GEMM" if engine == "bf16" else "fp32 FFMA engine"),
                     achieved=ach, peak=peaks["tf_sus"], unit="TFLOP/s", frac=ach / peaks["tf_sus"], traffic=None,
                     peak_source=peaks["source"] + ", sustained bf16", ms_per_step=conv_total_ms,
                     share_of_step=conv_total_ms / (ms / K), flops_per_step=flops_step)

@@ -164,6 +164,19 @@ int vxm_conv3d_tc_wgrad(const void* xa, const void* xb, const float* const* xf, 
                         int nplanar_x, const void* gz, const float* const* gf, const long long* gf_bstride,
                         int nplanar_g, float* grad_w, float* grad_b, void* work, int B, int D, int H, int W,
                         int Ca, int Cb, int up, int Cin_real, int Cg, int Cout_real, int kd, void* stream);
+/* ---- channels-last bf16 glue of the tensor-core U-Net engine (reference networks.py:126-138 and its autograd) ----
+ * All tensors bf16 (B,D,H,W,C), C % 8 == 0.  (Dc,Hc,Wc) are the COARSE dims; the fine tensor is (fd*Dc, 2Hc, 2Wc)
+ * with fd = 2 for nd == 3 and 1 for nd == 2. */
+int vxm_pool2_ndhwc_bf16(const void* x_fine, void* y_coarse, int B, int Dc, int Hc, int Wc, int C, int nd, void* stream);
+/* out_coarse = (sum over the 2^nd children of g_fine) * (act_coarse < 0 ? slope : 1); act_coarse may be NULL */
+int vxm_sumpool_mask_ndhwc_bf16(const void* g_fine, const void* act_coarse, void* out_coarse, int B, int Dc, int Hc,
+                                int Wc, int C, int nd, float slope, void* stream);
+/* out_fine = (g_skip_fine + [child is the first max of e_fine in its window] * g_pool_coarse) * (e_fine < 0 ? slope : 1);
+ * g_skip or g_pool may be NULL (not both) */
+int vxm_unpool_combine_ndhwc_bf16(const void* e_fine, const void* g_skip_fine, const void* g_pool_coarse, void* out_fine,
+                                  int B, int Dc, int Hc, int Wc, int C, int nd, float slope, void* stream);
+/* out[c] = sum_{b,v} x[b][c][v] for planar fp32 x (B,C,V), C <= 32; work: 128*C floats */
+int vxm_planar_channel_sums(const float* x, float* out, void* work, int B, int C, size_t V, void* stream);
 
 /* ---- MaxPool(2) / nearest Upsample(2) + concat: reference networks.py:83-85,130,137-138 ----
  * pool factor is 2 on H, W and on D when D > 1 (nd == 3).  idx (uint8, same shape as y) stores the

@@ -69,11 +69,38 @@ def resize_transform(x, vel_resize):
 DEFAULT_FEATURES = ((16, 32, 32, 32), (32, 32, 32, 32, 32, 16, 16))  # py/utils.py:16-21
 
 
+class _RoundBf16(torch.autograd.Function):
+    """bf16 storage emulation with a straight-through gradient (used to mirror the tensor-core engine, which keeps
+    activations and weight operands in bf16 and accumulates in fp32)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+_EMULATE_BF16 = [False]
+
+
+def emulate_bf16(flag):
+    """Test switch: round conv operands / activations to bf16 exactly where the tensor-core engine stores bf16."""
+    _EMULATE_BF16[0] = bool(flag)
+
+
 def _conv(x, sd, prefix, leaky):
     nd = x.dim() - 2
     fn = (F.conv1d, F.conv2d, F.conv3d)[nd - 1]
-    y = fn(x, sd[prefix + ".weight"], sd[prefix + ".bias"], stride=1, padding=1)
-    return F.leaky_relu(y, 0.2) if leaky else y
+    w = sd[prefix + ".weight"]
+    if _EMULATE_BF16[0]:
+        x, w = _RoundBf16.apply(x), _RoundBf16.apply(w)
+    y = fn(x, w, sd[prefix + ".bias"], stride=1, padding=1)
+    y = F.leaky_relu(y, 0.2) if leaky else y
+    if _EMULATE_BF16[0] and leaky:
+        y = _RoundBf16.apply(y)          # activations are stored in bf16; the flow head output stays fp32
+    return y
 
 
 def unet_plan(cfg):

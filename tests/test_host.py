@@ -131,14 +131,14 @@ assert float(grad[0]) == 3.0                      # SUM over ranks; 1/world is a
 m = vdist.max_over_ranks(float(rank), torch.device("cpu"))
 assert m == 1.0
 dist.barrier()
-print("rank", rank, "ok")
+open(os.path.join(os.environ["VXM_OUT"], "ok_%d" % rank), "w").write("ok")
 '''
 
 
 def test_data_parallel_logic_gloo_world2(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(DIST_WORKER)
-    env = dict(os.environ, VXM_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
+    env = dict(os.environ, VXM_ROOT=ROOT, MASTER_ADDR="127.0.0.1", VXM_OUT=str(tmp_path))
     import socket
     with socket.socket() as sk:
         sk.bind(("127.0.0.1", 0))
@@ -147,4 +147,4 @@ def test_data_parallel_logic_gloo_world2(tmp_path):
            "--master-port", str(port), str(script)]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+    assert (tmp_path / "ok_0").exists() and (tmp_path / "ok_1").exists()

@@ -33,8 +33,14 @@ struct WgradTcArgs {
   int tiles_h, tiles_w, dchunk, nchunks, nitems, nslot;
 };
 
-template <int KD, int NP>
+// STK > 0 (= channel chunks per slab, 1/2/4; KD == 3 only): the three kd taps are STACKED along M — the slabs of
+// consecutive input slices are adjacent in shared memory, so one operand of 3*STK channel chunks (stride = one plane)
+// spans slices d-1, d, d+1 and a single MMA accumulates all three kd taps: 72 MMAs per 128-voxel tile instead of 216.
+// The ring carries two mirror slots (copies of slots 0 and 1) so that a 3-slab window never wraps.
+template <int KD, int NP, int STK>
 __global__ void __launch_bounds__(WNTHREADS, 1) wgrad_tc_kernel(const WgradTcArgs a) {
+  constexpr int SM = STK == 0 ? 64 : (3 * STK <= 8 ? 64 : 128);   // MMA M
+  constexpr int NMIRROR = STK ? 2 : 0;
   extern __shared__ __align__(128) uint8_t smem[];
   const bool px = a.nplanar_x > 0, pg = a.nplanar_g > 0;
   const int nc8 = px ? 1 : (a.Ca + a.Cb) / 8;
@@ -44,7 +50,7 @@ __global__ void __launch_bounds__(WNTHREADS, 1) wgrad_tc_kernel(const WgradTcArg
   uint8_t* s_slab = smem;
   const int WNSLOT = a.nslot;
   // tail padding so that the M=64 operand (8 channel planes) never reads past the allocation
-  uint8_t* s_g = s_slab + WNSLOT * slab_bytes + 8 * WPLANE;
+  uint8_t* s_g = s_slab + (WNSLOT + NMIRROR) * slab_bytes + 16 * WPLANE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_g + WNG * gt_bytes + 4 * GPLANE);
   uint64_t* xfull = bars;
   uint64_t* xempty = bars + WMAXSLOT;
@@ -54,8 +60,8 @@ __global__ void __launch_bounds__(WNTHREADS, 1) wgrad_tc_kernel(const WgradTcArg
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int T = KD * 9, npairs = (T + 1) / 2;
-  const uint32_t need_cols = (uint32_t)npairs * NP;
+  const int T = KD * 9, npairs = STK ? 5 : (T + 1) / 2;
+  const uint32_t need_cols = (STK && SM == 128) ? 9u * NP : (uint32_t)npairs * NP;
   const uint32_t tmem_cols = need_cols <= 32 ? 32u : need_cols <= 64 ? 64u : need_cols <= 128 ? 128u : need_cols <= 256 ? 256u : 512u;
 
   if (threadIdx.x == 0) {
@@ -136,6 +142,7 @@ __global__ void __launch_bounds__(WNTHREADS, 1) wgrad_tc_kernel(const WgradTcArg
               const bool ok = dok && soff[k] >= 0;
               const __nv_bfloat16* src = ok ? ((soff[k] & 1) ? baseB : baseA) + (soff[k] >> 1) : dummy;
               cp_async16(slab + doff[k], src, ok ? 16u : 0u);
+              if (STK && slot < NMIRROR) cp_async16(slab + (size_t)WNSLOT * slab_bytes + doff[k], src, ok ? 16u : 0u);
             }
           }
           cp_async_arrive_noinc(&xfull[slot]);
@@ -149,7 +156,9 @@ __global__ void __launch_bounds__(WNTHREADS, 1) wgrad_tc_kernel(const WgradTcArg
               const size_t off = ((size_t)ds * a.H + h) * a.W + w;
               for (int p = 0; p < a.nplanar_x; ++p) v[p] = __ldg(a.xf[p] + (size_t)b * a.xf_bs[p] + off);
             }
-            *reinterpret_cast<uint4*>(slab + row * 16) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), 0u, 0u);
+            const uint4 q = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), 0u, 0u);
+            *reinterpret_cast<uint4*>(slab + row * 16) = q;
+            if (STK && slot < NMIRROR) *reinterpret_cast<uint4*>(slab + (size_t)WNSLOT * slab_bytes + row * 16) = q;
           }
           fence_proxy_async();
           mbar_arrive(&xfull[slot]);
@@ -217,6 +226,30 @@ __global__ void __launch_bounds__(WNTHREADS, 1) wgrad_tc_kernel(const WgradTcArg
           for (int kd = 0; kd < KD; ++kd)
             adesc_kd[kd] = make_desc_mnmajor_noswz(slab_u32 + ((xbase + j + kd) % WNSLOT) * slab_bytes, (uint32_t)WSW * 16u, (uint32_t)WPLANE);
           const uint32_t acc0 = first_tile ? 0u : 1u;
+          if constexpr (STK > 0) {
+            constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(SM >> 4) << 24);
+            // window = slabs of slices j, j+1, j+2, contiguous thanks to the mirror slots
+            const uint64_t adesc_w = make_desc_mnmajor_noswz(slab_u32 + ((xbase + j) % WNSLOT) * slab_bytes, (uint32_t)WSW * 16u, (uint32_t)WPLANE);
+            if (elect_one()) {
+#pragma unroll
+              for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                  const int t9 = kh * 3 + kw;
+                  const uint32_t tmem_d = SM == 128 ? tmem_base + (uint32_t)(t9 * NP)
+                                                    : tmem_base + ((uint32_t)((t9 & 1) * 16) << 16) + (uint32_t)((t9 >> 1) * NP);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const uint64_t adesc = adesc_w + (uint64_t)((kh + 2 * i) * WSW + kw);
+                    const uint64_t bdesc = bdesc0 + (uint64_t)(2 * i * 128 / 16);
+                    umma_f16(tmem_d, adesc, bdesc, idesc_s, i == 0 ? acc0 : 1u);
+                  }
+                }
+              }
+              umma_commit(&xempty[(xbase + j) % WNSLOT]);
+              umma_commit(&gempty[gs]);
+            }
+          } else
           if (elect_one()) {
 #pragma unroll
             for (int kd = 0; kd < KD; ++kd) {
@@ -260,7 +293,48 @@ __global__ void __launch_bounds__(WNTHREADS, 1) wgrad_tc_kernel(const WgradTcArg
     // ================================ EPILOGUE: TMEM -> partial[cta] ================================
     float* part = a.partial + (size_t)blockIdx.x * T * 64 * NP;
     const int ci = warp * 16 + (lane & 15);
-    if (has_work) {
+    if (has_work && STK > 0 && SM == 128) {
+      // rows = kd * (8*STK) + ci on TMEM lanes 0..127; columns t9 * NP
+      mbar_wait(done, 0);
+      tc_fence_after();
+      const int rowm = warp * 32 + lane, kd = rowm / (8 * STK), cis = rowm % (8 * STK);
+      for (int t9 = 0; t9 < 9; ++t9) {
+        for (int c0 = 0; c0 < NP; c0 += 8) {
+          uint32_t r[8];
+          const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)t9 * NP + c0;
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                       : "r"(taddr) : "memory");
+          tmem_ld_wait();
+          if (kd < 3) {
+            float4* o = reinterpret_cast<float4*>(part + ((size_t)(kd * 9 + t9) * 64 + cis) * NP + c0);
+            o[0] = make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
+            o[1] = make_float4(__uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
+          }
+        }
+      }
+    } else if (has_work && STK > 0) {
+      // M = 64: rows kd * (8*STK) + ci on lanes (m % 16) + 32 * (m / 16); tap pairs share columns (lane offset 16)
+      mbar_wait(done, 0);
+      tc_fence_after();
+      const int rowm = warp * 16 + (lane & 15), kd = rowm / (8 * STK), cis = rowm % (8 * STK);
+      for (int p = 0; p < 5; ++p) {
+        const int t9 = 2 * p + (lane >> 4);
+        for (int c0 = 0; c0 < NP; c0 += 8) {
+          uint32_t r[8];
+          const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)p * NP + c0;
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                       : "r"(taddr) : "memory");
+          tmem_ld_wait();
+          if (t9 < 9 && kd < 3) {
+            float4* o = reinterpret_cast<float4*>(part + ((size_t)(kd * 9 + t9) * 64 + cis) * NP + c0);
+            o[0] = make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
+            o[1] = make_float4(__uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
+          }
+        }
+      }
+    } else if (has_work) {
       mbar_wait(done, 0);
       tc_fence_after();
       for (int p = 0; p < npairs; ++p) {
@@ -383,20 +457,26 @@ extern "C" int vxm_conv3d_tc_wgrad(const void* xa, const void* xb, const float* 
   a.partial = (float*)work;
   int nc8 = nplanar_x > 0 ? 1 : Cin / 8, ncg = nplanar_g > 0 ? 1 : Cg / 8;
   VXM_REQUIRE(nc8 * WROWS <= WKMAX * WNLOADER && ncg * 128 <= 4 * WNLOADER, "conv3d_tc_wgrad: tile too large for the loader table");
-  size_t fixed = 8 * WPLANE + (size_t)WNG * ncg * GPLANE + 4 * GPLANE + 512;
+  const int stk = (kd == 3 && (nc8 == 1 || nc8 == 2 || nc8 == 4)) ? nc8 : 0;
+  size_t fixed = 16 * WPLANE + (size_t)(stk ? 2 : 0) * nc8 * WPLANE + (size_t)WNG * ncg * GPLANE + 4 * GPLANE + 512;
   int nslot = (int)((200 * 1024 - fixed) / ((size_t)nc8 * WPLANE));
   if (nslot > WMAXSLOT) nslot = WMAXSLOT;
   VXM_REQUIRE(nslot >= 4, "conv3d_tc_wgrad: not enough shared memory for the slab ring");
   a.nslot = nslot;
   size_t smem = fixed + (size_t)nslot * nc8 * WPLANE;
   cudaStream_t st = as_stream(stream);
-#define VXM_WG_LAUNCH(KD_, NP_)                                                                                        \
-  do {                                                                                                                 \
-    VXM_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<KD_, NP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    wgrad_tc_kernel<KD_, NP_><<<grid, WNTHREADS, smem, st>>>(a);                                                        \
+#define VXM_WG_LAUNCH(KD_, NP_, STK_)                                                                                        \
+  do {                                                                                                                       \
+    VXM_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<KD_, NP_, STK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    wgrad_tc_kernel<KD_, NP_, STK_><<<grid, WNTHREADS, smem, st>>>(a);                                                        \
   } while (0)
-  if (kd == 3) { if (a.NP == 8) VXM_WG_LAUNCH(3, 8); else if (a.NP == 16) VXM_WG_LAUNCH(3, 16); else VXM_WG_LAUNCH(3, 32); }
-  else { if (a.NP == 8) VXM_WG_LAUNCH(1, 8); else if (a.NP == 16) VXM_WG_LAUNCH(1, 16); else VXM_WG_LAUNCH(1, 32); }
+#define VXM_WG_NP(KD_, STK_)                                                                                            \
+  do { if (a.NP == 8) VXM_WG_LAUNCH(KD_, 8, STK_); else if (a.NP == 16) VXM_WG_LAUNCH(KD_, 16, STK_); else VXM_WG_LAUNCH(KD_, 32, STK_); } while (0)
+  if (kd == 3) {
+    if (stk == 1) VXM_WG_NP(3, 1); else if (stk == 2) VXM_WG_NP(3, 2); else if (stk == 4) VXM_WG_NP(3, 4); else VXM_WG_NP(3, 0);
+  } else {
+    VXM_WG_NP(1, 0);
+  }
   int rc = check_launch("conv3d_tc_wgrad");
   if (rc) return rc;
   int T = kd * 9;

@@ -1,0 +1,265 @@
+"""The tensor-core (bf16 operands / fp32 accumulation) execution engine of Unet + flow head.
+
+`unet_flow(model, source, target)` computes `model.flow(model.unet_model(cat(source, target)))`
+(reference voxelmorph/torch/networks.py:253-257) entirely with the tcgen05 convolution kernels and the
+channels-last bf16 glue kernels: every activation between the fp32 input images and the fp32 flow field is a
+bf16 (B,D,H,W,C) tensor, the concat / upsample / bias / LeakyReLU / LeakyReLU-derivative are fused into the
+convolution kernels, and the backward pass (dgrad, wgrad, pooling and skip routing) is written out by hand —
+torch autograd only sees one node.  Parameters stay the module's own fp32 `nn.Parameter`s.
+"""
+import torch
+
+from . import _lib, tc
+
+_weights_epoch = 0
+
+
+def bump_weights_epoch():
+    """Called by optimizers that update parameters behind torch's back (FusedAdam) so packed copies refresh."""
+    global _weights_epoch
+    _weights_epoch += 1
+
+
+class _PackCache:
+    def __init__(self):
+        self.c = {}
+
+    def get(self, w, key, fn):
+        k = (id(w), key)
+        stamp = (w.data_ptr(), w._version, _weights_epoch)
+        hit = self.c.get(k)
+        if hit is None or hit[0] != stamp:
+            hit = (stamp, fn())
+            self.c[k] = hit
+        return hit[1]
+
+
+_cache = _PackCache()
+
+
+def _check_cout(c, what):
+    if c not in (8, 16, 32):
+        raise _lib.VxmError("bf16 tensor-core engine: %s has %d channels; supported feature counts are 8, 16 and 32 "
+                            "(use VXM_B200_CONV_ENGINE=f32 for other U-Net shapes)" % (what, c))
+
+
+def _pool(x, nd):
+    lib = _lib.load()
+    B, D, H, W, C = x.shape
+    Dc = D // 2 if nd == 3 else D
+    y = torch.empty((B, Dc, H // 2, W // 2, C), dtype=torch.bfloat16, device=x.device)
+    if (nd == 3 and D % 2) or H % 2 or W % 2:
+        raise _lib.VxmError("bf16 engine: odd sizes cannot be pooled (U-Net shapes must be divisible by 2 per level)")
+    _lib.check(lib.vxm_pool2_ndhwc_bf16(_lib.ptr(x), _lib.ptr(y), B, Dc, H // 2, W // 2, C, nd, _lib.stream_ptr()), "vxm_pool2_ndhwc_bf16")
+    return y
+
+
+def _sumpool_mask(g_fine, act_coarse, nd, slope):
+    lib = _lib.load()
+    B, Dc, Hc, Wc, C = act_coarse.shape
+    out = torch.empty_like(act_coarse)
+    _lib.check(lib.vxm_sumpool_mask_ndhwc_bf16(_lib.ptr(g_fine), _lib.ptr(act_coarse), _lib.ptr(out), B, Dc, Hc, Wc, C, nd, slope,
+                                               _lib.stream_ptr()), "vxm_sumpool_mask_ndhwc_bf16")
+    return out
+
+
+def _unpool_combine(e_fine, g_skip, g_pool, nd, slope):
+    lib = _lib.load()
+    B, D, H, W, C = e_fine.shape
+    Dc = D // 2 if nd == 3 else D
+    out = torch.empty_like(e_fine)
+    _lib.check(lib.vxm_unpool_combine_ndhwc_bf16(_lib.ptr(e_fine), _lib.ptr(g_skip), _lib.ptr(g_pool), _lib.ptr(out), B, Dc, H // 2,
+                                                 W // 2, C, nd, slope, _lib.stream_ptr()), "vxm_unpool_combine_ndhwc_bf16")
+    return out
+
+
+class _Conv:
+    """One convolution of the tape: inputs, output, parameters."""
+    __slots__ = ("w", "b", "planar", "xa", "xb", "up", "out", "slope", "cin", "cout", "a_id", "b_id", "out_id", "planar_out")
+
+
+def _run_conv(cv, kd):
+    """Forward of one tape entry."""
+    wpk, NP = _cache.get(cv.w, "fwd", lambda: tc.pack_weights(cv.w.detach()))
+    return tc.conv_fwd(cv.xa, cv.xb, wpk, NP, cv.b.detach() if cv.b is not None else None, cv.cout, kd, up=cv.up, planar=cv.planar,
+                       out_fp32_planar=cv.planar_out, slope=cv.slope)
+
+
+def forward_tape(model, source, target):
+    """Runs Unet + flow head, returns (flow fp32 (B,nd,*vol), tape)."""
+    unet = model.unet_model
+    nd = source.dim() - 2
+    kd = 3 if nd == 3 else 1
+    _lib.require_cuda(source, target, what="VxmDense")
+    source, target = _lib.contig(source), _lib.contig(target)
+    planes = [source[:, i:i + 1] for i in range(source.shape[1])] + [target[:, i:i + 1] for i in range(target.shape[1])]
+    if len(planes) > 4:
+        raise _lib.VxmError("bf16 engine: at most 4 input feature planes (src_feats + trg_feats)")
+    tape = []            # list of ("conv", _Conv) / ("pool", in_id, out_id)
+    tensors = {}         # id -> bf16 NDHWC tensor
+    producer = {}        # id -> "conv" | "pool"
+    next_id = [0]
+
+    def new_id():
+        next_id[0] += 1
+        return next_id[0]
+
+    def conv(block_main, slope, planar=None, a_id=None, b_id=None, up=False, planar_out=False):
+        cv = _Conv()
+        cv.w, cv.b = block_main.weight, block_main.bias
+        cv.planar = planar
+        cv.xa = tensors[a_id] if a_id is not None else None
+        cv.xb = tensors[b_id] if b_id is not None else None
+        cv.up, cv.slope, cv.planar_out = up, slope, planar_out
+        cv.cout, cv.cin = cv.w.shape[0], cv.w.shape[1]
+        cv.a_id, cv.b_id = a_id, b_id
+        if not planar_out:
+            _check_cout(cv.cout, "a U-Net convolution output")
+        if planar is None:
+            ca = 0 if cv.xa is None else cv.xa.shape[-1]
+            cb = 0 if cv.xb is None else cv.xb.shape[-1]
+            if ca + cb != cv.cin or (ca + cb) % 16 or ca + cb > 64:
+                raise _lib.VxmError("bf16 engine: unsupported convolution input channels %d (+%d); need a multiple of 16, at most 64"
+                                    % (ca, cb))
+        out = _run_conv(cv, kd)
+        cv.out = out
+        cv.out_id = new_id()
+        if not planar_out:
+            tensors[cv.out_id] = out
+            producer[cv.out_id] = "conv"
+        tape.append(("conv", cv))
+        return cv.out_id
+
+    def pool(in_id):
+        y = _pool(tensors[in_id], nd)
+        oid = new_id()
+        tensors[oid] = y
+        producer[oid] = "pool"
+        tape.append(("pool", in_id, oid))
+        return oid
+
+    cur = None           # current tensor id (None = the raw planar input)
+    skips = [None]
+    first = True
+    for level, convs in enumerate(unet.encoder):
+        for blk in convs:
+            slope = blk.activation.negative_slope
+            if first:
+                cur = conv(blk.main, slope, planar=planes)
+                first = False
+            else:
+                cur = conv(blk.main, slope, a_id=cur)
+        skips.append(cur)
+        cur = pool(cur)
+    pending_up = None    # (a_id, skip_id) to be consumed by the next convolution as a fused upsample+concat
+    for level, convs in enumerate(unet.decoder):
+        for blk in convs:
+            slope = blk.activation.negative_slope
+            if pending_up is not None:
+                cur = conv(blk.main, slope, a_id=pending_up[0], b_id=pending_up[1], up=True)
+                pending_up = None
+            else:
+                cur = conv(blk.main, slope, a_id=cur)
+        if not unet.half_res or level < (unet.nb_levels - 2):
+            pending_up = (cur, skips.pop())
+    for blk in unet.remaining:
+        slope = blk.activation.negative_slope
+        if pending_up is not None:
+            cur = conv(blk.main, slope, a_id=pending_up[0], b_id=pending_up[1], up=True)
+            pending_up = None
+        else:
+            cur = conv(blk.main, slope, a_id=cur)
+    # flow head (no activation, fp32 planar output)
+    if pending_up is not None:
+        fid = conv(model.flow, None, a_id=pending_up[0], b_id=pending_up[1], up=True, planar_out=True)
+    else:
+        fid = conv(model.flow, None, a_id=cur, planar_out=True)
+    flow = tape[-1][1].out
+    if nd == 2:
+        flow = flow.squeeze(2)
+    return flow, dict(tape=tape, tensors=tensors, producer=producer, nd=nd, kd=kd)
+
+
+def backward_tape(ctx, g_flow):
+    """Hand-written backward over the tape.  Returns {param: grad}."""
+    lib = _lib.load()
+    tape, tensors, producer, nd, kd = ctx["tape"], ctx["tensors"], ctx["producer"], ctx["nd"], ctx["kd"]
+    g_flow = _lib.contig(g_flow.float())
+    if nd == 2:
+        g_flow = g_flow.unsqueeze(2)
+    gz = {}       # conv-output id -> masked gradient (bf16 NDHWC)
+    graw = {}     # pool-output id -> raw gradient
+    gskip = {}    # encoder-output id -> raw skip gradient
+    grads = {}
+    dev = g_flow.device
+    for entry in reversed(tape):
+        if entry[0] == "pool":
+            _, in_id, out_id = entry
+            e = tensors[in_id]
+            gz[in_id] = _unpool_combine(e, gskip.pop(in_id, None), graw.pop(out_id), nd, _slope_of(ctx, in_id))
+            continue
+        cv = entry[1]
+        if cv.planar_out:
+            g_planes = [g_flow[:, i:i + 1] for i in range(g_flow.shape[1])]
+            gw, _ = tc.conv_wgrad(cv.xa, cv.xb, None, cv.cin, cv.cout, kd, up=cv.up, planar_g=g_planes, need_bias=False)
+            gb = torch.empty(cv.cout, dtype=torch.float32, device=dev)
+            work = torch.empty(128 * cv.cout, dtype=torch.float32, device=dev)
+            V = g_flow[0, 0].numel()
+            _lib.check(lib.vxm_planar_channel_sums(_lib.ptr(g_flow), _lib.ptr(gb), _lib.ptr(work), g_flow.shape[0], cv.cout, V,
+                                                   _lib.stream_ptr()), "vxm_planar_channel_sums")
+            g_in_planar, g_in = g_planes, None
+        else:
+            g_in = gz.pop(cv.out_id)
+            gw, gb = tc.conv_wgrad(cv.xa, cv.xb, g_in, cv.cin, cv.cout, kd, up=cv.up, planar_x=cv.planar)
+            g_in_planar = None
+        grads[cv.w] = gw.squeeze(2) if nd == 2 else gw
+        if cv.b is not None:
+            grads[cv.b] = gb
+        # ---- dgrad ----
+        if cv.planar is not None:
+            continue       # first layer: the images need no gradient
+        w = cv.w.detach()
+        if cv.b_id is None:
+            t = cv.a_id
+            wpk, NP = _cache.get(cv.w, "dgrad", lambda: tc.pack_weights(w, transposed=True))
+            if producer[t] == "conv":
+                gz[t] = tc.conv_fwd(g_in, None, wpk, NP, None, cv.cin, kd, planar=g_in_planar, slope=_slope_of(ctx, t), mask=tensors[t])
+            else:
+                graw[t] = tc.conv_fwd(g_in, None, wpk, NP, None, cv.cin, kd, planar=g_in_planar)
+        else:
+            ca = cv.xa.shape[-1]
+            wa, NPa = _cache.get(cv.w, "dgrad_a", lambda: tc.pack_weights(w[:, :ca].contiguous(), transposed=True))
+            wb, NPb = _cache.get(cv.w, "dgrad_b", lambda: tc.pack_weights(w[:, ca:].contiguous(), transposed=True))
+            g_up = tc.conv_fwd(g_in, None, wa, NPa, None, ca, kd, planar=g_in_planar)             # grad wrt upsample(a), fine res
+            gz[cv.a_id] = _sumpool_mask(g_up, tensors[cv.a_id], nd, _slope_of(ctx, cv.a_id))
+            del g_up
+            gskip[cv.b_id] = tc.conv_fwd(g_in, None, wb, NPb, None, cv.cin - ca, kd, planar=g_in_planar)
+    return grads
+
+
+def _slope_of(ctx, tid):
+    for entry in ctx["tape"]:
+        if entry[0] == "conv" and entry[1].out_id == tid:
+            s = entry[1].slope
+            return -1.0 if s is None else float(s)
+    return -1.0
+
+
+class _UnetFlowFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, source, target, *params):
+        flow, tape = forward_tape(model, source, target)
+        ctx.tape = tape
+        ctx.params = params
+        return flow
+
+    @staticmethod
+    def backward(ctx, g_flow):
+        grads = backward_tape(ctx.tape, g_flow)
+        ctx.tape = None
+        return (None, None, None) + tuple(grads.get(p) for p in ctx.params)
+
+
+def unet_flow(model, source, target):
+    params = [p for p in list(model.unet_model.parameters()) + list(model.flow.parameters())]
+    return _UnetFlowFn.apply(model, source, target, *params)

@@ -189,9 +189,14 @@ class VxmDense(LoadableModel):
         self.transformer = layers.SpatialTransformer(inshape)
 
     def forward(self, source, target, registration=False):
-        x = ops.upsample_free_cat(source, target)
-        x = self.unet_model(x)
-        flow_field = self.flow(x)
+        if ops.conv_engine() == 'bf16':
+            # tensor-core engine: Unet + flow head as one hand-written forward/backward (engine_bf16.py)
+            from . import engine_bf16
+            flow_field = engine_bf16.unet_flow(self, source, target)
+        else:
+            x = ops.upsample_free_cat(source, target)
+            x = self.unet_model(x)
+            flow_field = self.flow(x)
 
         pos_flow = flow_field
         if self.resize:

@@ -72,3 +72,5 @@ class FusedAdam:
         _lib.check(lib.vxm_adam_step(_lib.ptr(self.fp.flat), _lib.ptr(self.fp.grad), _lib.ptr(self.m), _lib.ptr(self.v),
                                      self.fp.numel, self.step_count, self.lr, self.betas[0], self.betas[1], self.eps,
                                      self.weight_decay, self.grad_scale, _lib.stream_ptr()), "vxm_adam_step")
+        from . import engine_bf16
+        engine_bf16.bump_weights_epoch()   # parameters changed behind torch's version counter
