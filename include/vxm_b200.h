@@ -175,6 +175,10 @@ int vxm_sumpool_mask_ndhwc_bf16(const void* g_fine, const void* act_coarse, void
  * g_skip or g_pool may be NULL (not both) */
 int vxm_unpool_combine_ndhwc_bf16(const void* e_fine, const void* g_skip_fine, const void* g_pool_coarse, void* out_fine,
                                   int B, int Dc, int Hc, int Wc, int C, int nd, float slope, void* stream);
+/* out (B,V,8) bf16 <- up to 8 planar fp32 volumes (channel c = planes[c], batch stride bstrides[c] floats); unused
+ * channels are zero.  Feeds the fp32 images / the fp32 flow gradient to the tensor-core kernels. */
+int vxm_planar_to_ndhwc8_bf16(const float* const* planes, const long long* bstrides, int nplanes, void* out, int B,
+                              size_t V, void* stream);
 /* out[c] = sum_{b,v} x[b][c][v] for planar fp32 x (B,C,V), C <= 32; work: 128*C floats */
 int vxm_planar_channel_sums(const float* x, float* out, void* work, int B, int C, size_t V, void* stream);
 

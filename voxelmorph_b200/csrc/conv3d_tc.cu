@@ -55,9 +55,12 @@ template <int KD, int NK16, int NP>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const ConvTcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const bool planar = a.nplanar > 0;
+  // "half-K" inputs (8 real channels: the planar fp32 sources, or an 8-channel bf16 tensor): one staged plane;
+  // the second 16-byte K chunk of the single K step reads a shared all-zero plane
+  const bool halfk = planar || (a.Ca + a.Cb == 8);
   const int Cin = NK16 * 16;
   constexpr int nk16 = NK16;
-  const int nc8 = planar ? 1 : Cin / 8;            // staged planes (planar mode: plane 0 data + a shared zero plane)
+  const int nc8 = halfk ? 1 : Cin / 8;
   const uint32_t slab_bytes = (uint32_t)nc8 * PLANE;
   uint8_t* s_w = smem;
   uint8_t* s_slab = smem + ((a.wbytes + 127u) & ~127u);
@@ -178,7 +181,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const ConvTcArgs a
     {
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t slab_u32 = smem_u32(s_slab), w_u32 = smem_u32(s_w);
-      const uint32_t a_lbo = planar ? (smem_u32(s_zero) - slab_u32) : (uint32_t)PLANE;
+      const uint32_t a_lbo = halfk ? (smem_u32(s_zero) - slab_u32) : (uint32_t)PLANE;
       constexpr uint32_t b_tile16 = (uint32_t)NP * 32u / 16u;
       mbar_wait(wbar, 0);
       const uint64_t bdesc0 = make_desc_kmajor_noswz(w_u32, (uint32_t)NP * 16u, 128u);
@@ -207,7 +210,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const ConvTcArgs a
           for (int kd = 0; kd < KD; ++kd) {
             const uint32_t sl = (cnt_base + j + kd) % NSLOT;
             // planar mode: the second K chunk (channels 8..15) reads the shared all-zero plane
-            adesc_kd[kd] = make_desc_kmajor_noswz(slab_u32 + sl * slab_bytes, planar ? (a_lbo - sl * slab_bytes) : a_lbo, (uint32_t)SW * 16u);
+            adesc_kd[kd] = make_desc_kmajor_noswz(slab_u32 + sl * slab_bytes, halfk ? (a_lbo - sl * slab_bytes) : a_lbo, (uint32_t)SW * 16u);
           }
           if (elect_one()) {
 #pragma unroll
@@ -372,11 +375,11 @@ extern "C" int vxm_conv3d_tc_fwd(const void* xa, const void* xb, const float* co
     Cin = 16;
   } else {
     VXM_REQUIRE(xa || xb, "conv3d_tc_fwd: no input");
-    VXM_REQUIRE(Ca % 8 == 0 && Cb % 8 == 0 && (Ca + Cb) % 16 == 0 && Ca + Cb >= 16 && Ca + Cb <= 64,
+    VXM_REQUIRE(Ca % 8 == 0 && Cb % 8 == 0 && ((Ca + Cb) % 16 == 0 || Ca + Cb == 8) && Ca + Cb >= 8 && Ca + Cb <= 64,
                 "conv3d_tc_fwd: channel counts (%d,%d) unsupported", Ca, Cb);
     VXM_REQUIRE((Ca == 0 || xa) && (Cb == 0 || xb), "conv3d_tc_fwd: missing source tensor");
     VXM_REQUIRE(!up || (H % 2 == 0 && W % 2 == 0 && (kd == 1 || D % 2 == 0)), "conv3d_tc_fwd: upsampled source needs even sizes");
-    Cin = Ca + Cb;
+    Cin = Ca + Cb == 8 ? 16 : Ca + Cb;
   }
   a.xa = (const __nv_bfloat16*)xa; a.xb = (const __nv_bfloat16*)xb; a.wpk = (const __nv_bfloat16*)wpk; a.bias = bias;
   a.out = out; a.mask = (const __nv_bfloat16*)mask;
@@ -391,8 +394,8 @@ extern "C" int vxm_conv3d_tc_fwd(const void* xa, const void* xb, const float* co
   long long ni = items(dchunk);
   VXM_REQUIRE(ni < (1LL << 31), "conv3d_tc_fwd: too many tiles");
   a.nitems = (int)ni;
-  a.wbytes = (uint32_t)vxm_conv3d_tc_packed_bytes(Cin, np, kd);
-  int nc8 = nplanar > 0 ? 1 : Cin / 8;
+  a.wbytes = (uint32_t)vxm_conv3d_tc_packed_bytes(Cin, np, kd);   // Cin is rounded up to the K step (16)
+  int nc8 = (nplanar > 0 || Ca + Cb == 8) ? 1 : Cin / 8;
   VXM_REQUIRE(nc8 * ROWS <= KMAX * NLOADER, "conv3d_tc_fwd: slab too large for the loader table");
   size_t fixed = ((a.wbytes + 127u) & ~127u) + PLANE + 256;
   int nslot = (int)((227 * 1024 - fixed) / ((size_t)nc8 * PLANE));

@@ -29,6 +29,7 @@ struct WgradTcArgs {
   const __nv_bfloat16* gz; int Cg;
   const float* gf[4]; long long gf_bs[4]; int nplanar_g;
   float* partial;
+  float* bias_partial;   // [grid][NP]
   int B, D, H, W, KD, NP;
   int tiles_h, tiles_w, dchunk, nchunks, nitems, nslot;
 };
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(WNTHREADS, 1) wgrad_tc_kernel(const WgradTcArg
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < WNSLOT; ++i) { mbar_init(&xfull[i], WNLOADER); mbar_init(&xempty[i], 1); }
-    for (int i = 0; i < WNG; ++i) { mbar_init(&gfull[i], WNLOADER); mbar_init(&gempty[i], 1); }
+    for (int i = 0; i < WNG; ++i) { mbar_init(&gfull[i], WNLOADER); mbar_init(&gempty[i], 1 + 128); }
     mbar_init(done, 1);
     fence_barrier_init();
   }
@@ -290,7 +291,38 @@ __global__ void __launch_bounds__(WNTHREADS, 1) wgrad_tc_kernel(const WgradTcArg
       __syncwarp();
     }
   } else {
-    // ================================ EPILOGUE: TMEM -> partial[cta] ================================
+    // ================================ EPILOGUE WARPS ================================
+    // While the tensor core works they fold the bias gradient (sum of gz over voxels) out of the staged gz tiles:
+    // thread r owns tile row r and accumulates its NP channels in registers.
+    float bsum[NP];
+#pragma unroll
+    for (int c = 0; c < NP; ++c) bsum[c] = 0.f;
+    if (has_work) {
+      uint32_t gcnt = 0;
+      const int rowi = warp * 32 + lane;
+      for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+        const int ch = (item / HW_tiles) % a.nchunks;
+        const int nd = min(ch * a.dchunk + a.dchunk, a.D) - ch * a.dchunk;
+        for (int j = 0; j < nd; ++j) {
+          const uint32_t gs = gcnt % WNG;
+          mbar_wait(&gfull[gs], (gcnt / WNG) & 1);
+          const uint8_t* gt = s_g + (size_t)gs * gt_bytes + rowi * 16;
+#pragma unroll
+          for (int c8 = 0; c8 < NP / 8; ++c8) {
+            const uint4 q = *reinterpret_cast<const uint4*>(gt + (size_t)c8 * GPLANE);
+            const __nv_bfloat162* hq = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __bfloat1622float2(hq[e]);
+              bsum[c8 * 8 + 2 * e] += f.x;
+              bsum[c8 * 8 + 2 * e + 1] += f.y;
+            }
+          }
+          mbar_arrive(&gempty[gs]);
+          ++gcnt;
+        }
+      }
+    }
     float* part = a.partial + (size_t)blockIdx.x * T * 64 * NP;
     const int ci = warp * 16 + (lane & 15);
     if (has_work && STK > 0 && SM == 128) {
@@ -356,6 +388,20 @@ __global__ void __launch_bounds__(WNTHREADS, 1) wgrad_tc_kernel(const WgradTcArg
     } else {
       for (int i = threadIdx.x; i < T * 64 * NP; i += 128) part[i] = 0.f;
     }
+    // bias partial of this CTA: deterministic reduction over the 128 rows through shared memory (the slab ring is idle now)
+    {
+      float* s_b = reinterpret_cast<float*>(s_slab);
+      const int rowi = warp * 32 + lane;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+      for (int c = 0; c < NP; ++c) s_b[rowi * (NP + 1) + c] = bsum[c];
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (rowi < NP) {
+        float t = 0.f;
+        for (int r2 = 0; r2 < 128; ++r2) t += s_b[r2 * (NP + 1) + rowi];
+        a.bias_partial[(size_t)blockIdx.x * NP + rowi] = t;
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -366,8 +412,14 @@ __global__ void __launch_bounds__(WNTHREADS, 1) wgrad_tc_kernel(const WgradTcArg
 }
 
 // gw[co][ci][tap] = sum_cta partial[cta][tap][ci][co]   (fixed order -> deterministic)
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ gw, int ncta, int T, int NP, int Cout, int Cin) {
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ gw, int ncta, int T, int NP, int Cout, int Cin,
+                                    const float* __restrict__ bias_partial, float* __restrict__ gb) {
   const int total = Cout * Cin * T;
+  if (gb && blockIdx.x == 0 && threadIdx.x < Cout) {
+    float acc = 0.f;
+    for (int c = 0; c < ncta; ++c) acc += bias_partial[(size_t)c * NP + threadIdx.x];
+    gb[threadIdx.x] = acc;
+  }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int tap = i % T, ci = (i / T) % Cin, co = i / (T * Cin);
     float acc = 0.f;
@@ -455,6 +507,7 @@ extern "C" int vxm_conv3d_tc_wgrad(const void* xa, const void* xb, const float* 
   int grid = a.nitems < nsm ? a.nitems : nsm;
   if (grid > 256) grid = 256;
   a.partial = (float*)work;
+  a.bias_partial = (float*)work + (size_t)256 * kd * 9 * 64 * 32;
   int nc8 = nplanar_x > 0 ? 1 : Cin / 8, ncg = nplanar_g > 0 ? 1 : Cg / 8;
   VXM_REQUIRE(nc8 * WROWS <= WKMAX * WNLOADER && ncg * 128 <= 4 * WNLOADER, "conv3d_tc_wgrad: tile too large for the loader table");
   const int stk = (kd == 3 && (nc8 == 1 || nc8 == 2 || nc8 == 4)) ? nc8 : 0;
@@ -481,20 +534,6 @@ extern "C" int vxm_conv3d_tc_wgrad(const void* xa, const void* xb, const float* 
   if (rc) return rc;
   int T = kd * 9;
   int total = Cout_real * Cin_real * T;
-  wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(a.partial, grad_w, grid, T, a.NP, Cout_real, Cin_real);
-  rc = check_launch("conv3d_tc_wgrad_reduce");
-  if (rc) return rc;
-  if (grad_b) {
-    VXM_REQUIRE(nplanar_g == 0, "conv3d_tc_wgrad: bias gradient of planar gz is computed by the caller");
-    float* bpart = (float*)work + (size_t)256 * T * 64 * 32;
-    size_t V = (size_t)B * D * H * W;
-    int nb = 1024;
-    VXM_REQUIRE(256 % Cg == 0, "conv3d_tc_wgrad: bias gradient needs Cg | 256");
-    bias_grad_partial_kernel<<<nb, 256, 0, st>>>(a.gz, bpart, V, Cg);
-    rc = check_launch("bias_grad_partial");
-    if (rc) return rc;
-    bias_grad_final_kernel<<<1, 32, 0, st>>>(bpart, grad_b, nb, Cg, Cout_real);
-    rc = check_launch("bias_grad_final");
-  }
-  return rc;
+  wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(a.partial, grad_w, grid, T, a.NP, Cout_real, Cin_real, a.bias_partial, grad_b);
+  return check_launch("conv3d_tc_wgrad_reduce");
 }

@@ -165,6 +165,23 @@ __global__ void planar_sum_final_kernel(const float* __restrict__ part, float* _
   out[c] = (float)acc;
 }
 
+struct PlanarSrc {
+  const float* p[8];
+  long long bstride[8];
+  int n;
+};
+// out[(b*V + v)*8 + c] = bf16(plane_c[b][v]) for c < n, 0 otherwise
+__global__ void __launch_bounds__(256) planar_to_ndhwc8_kernel(PlanarSrc src, __nv_bfloat16* __restrict__ out, int B, size_t V) {
+  size_t n = (size_t)B * V;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    size_t b = i / V, v = i - b * V;
+    V8 r;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) r.v[c] = c < src.n ? __ldg(src.p[c] + b * src.bstride[c] + v) : 0.f;
+    st8(out + i * 8, r);
+  }
+}
+
 static int make_pool_geom(int B, int Dc, int Hc, int Wc, int C, int nd, PoolGeom* g) {
   VXM_REQUIRE(B > 0 && Dc > 0 && Hc > 0 && Wc > 0 && C > 0 && C % 8 == 0, "ndhwc op: bad dimensions (C must be a multiple of 8)");
   VXM_REQUIRE(nd == 2 || nd == 3, "ndhwc op: nd must be 2 or 3");
@@ -220,4 +237,17 @@ extern "C" int vxm_planar_channel_sums(const float* x, float* out, void* work, i
   if (rc) return rc;
   planar_sum_final_kernel<<<1, 32, 0, as_stream(stream)>>>((const float*)work, out, C, nblk);
   return check_launch("planar_sum_final");
+}
+
+extern "C" int vxm_planar_to_ndhwc8_bf16(const float* const* planes, const long long* bstrides, int nplanes, void* out, int B, size_t V,
+                                         void* stream) {
+  VXM_REQUIRE(planes && bstrides && out && nplanes > 0 && nplanes <= 8 && B > 0 && V > 0, "planar_to_ndhwc8: bad argument");
+  PlanarSrc src{};
+  src.n = nplanes;
+  for (int i = 0; i < nplanes; ++i) { src.p[i] = planes[i]; src.bstride[i] = bstrides[i]; }
+  size_t n = (size_t)B * V;
+  size_t blocks = (n + 255) / 256;
+  size_t cap = (size_t)sm_count() * 16;
+  planar_to_ndhwc8_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, as_stream(stream)>>>(src, (__nv_bfloat16*)out, B, V);
+  return check_launch("planar_to_ndhwc8");
 }

@@ -90,6 +90,54 @@ __device__ __forceinline__ void adj_range(const AxisMap& m, int i, int& lo, int&
   hi = min(m.out - 1, (int)ceilf((float)(i + 1) * inv) + 1);
 }
 
+// Table-driven adjoint: each block first tabulates, for its 32 x 8 x 1 input indices, the (output index, weight)
+// pairs of the 1-D adjoint along every axis (at most ADJ_MAX per index), then every thread runs a pure
+// multiply-add loop over the outer product of its three short lists.
+constexpr int ADJ_MAX = 8;
+struct AdjList {
+  int n;
+  int o[ADJ_MAX];
+  float w[ADJ_MAX];
+};
+
+__global__ void __launch_bounds__(256) resize_bwd_table_kernel(const float* __restrict__ gout, float* __restrict__ gx, ResizeGeom g) {
+  __shared__ AdjList lx[32], ly[8], lz[1];
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int ix = blockIdx.x * 32 + threadIdx.x;
+  const int iy = blockIdx.y * 8 + threadIdx.y;
+  const int iz = blockIdx.z % g.mz.in, bc = blockIdx.z / g.mz.in;
+  if (tid < 41) {
+    const AxisMap& m = tid < 32 ? g.mx : (tid < 40 ? g.my : g.mz);
+    const int i = tid < 32 ? blockIdx.x * 32 + tid : (tid < 40 ? blockIdx.y * 8 + (tid - 32) : iz);
+    AdjList& L = tid < 32 ? lx[tid] : (tid < 40 ? ly[tid - 32] : lz[0]);
+    L.n = 0;
+    if (i < m.in) {
+      int lo, hi;
+      adj_range(m, i, lo, hi);
+      for (int o = lo; o <= hi; ++o) {
+        float w = adj_weight(m, i, o);
+        if (w != 0.f && L.n < ADJ_MAX) { L.o[L.n] = o; L.w[L.n] = w; ++L.n; }
+      }
+    }
+  }
+  __syncthreads();
+  if (ix >= g.mx.in || iy >= g.my.in) return;
+  const AdjList& X = lx[threadIdx.x];
+  const AdjList& Y = ly[threadIdx.y];
+  const AdjList& Z = lz[0];
+  const float* gb = gout + (size_t)bc * g.mz.out * g.my.out * g.mx.out;
+  float acc = 0.f;
+  for (int a = 0; a < Z.n; ++a) {
+    for (int b = 0; b < Y.n; ++b) {
+      const float* r = gb + ((size_t)Z.o[a] * g.my.out + Y.o[b]) * g.mx.out;
+      float racc = 0.f;
+      for (int c = 0; c < X.n; ++c) racc += X.w[c] * __ldg(r + X.o[c]);
+      acc += Z.w[a] * Y.w[b] * racc;
+    }
+  }
+  gx[(((size_t)bc * g.mz.in + iz) * g.my.in + iy) * g.mx.in + ix] = acc * (g.pre * g.post);
+}
+
 __global__ void __launch_bounds__(256) resize_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gx, ResizeGeom g) {
   int ix = blockIdx.x * 32 + threadIdx.x;
   int iy = blockIdx.y * 8 + threadIdx.y;
@@ -147,6 +195,8 @@ extern "C" int vxm_resize_bwd(const float* grad_out, float* grad_x, int B, int C
   VXM_REQUIRE(grad_out && grad_x, "resize_bwd: null pointer");
   ResizeGeom g{make_map(Di, Do), make_map(Hi, Ho), make_map(Wi, Wo), B * C, pre, post};
   dim3 block(32, 8, 1), grid((Wi + 31) / 32, (Hi + 7) / 8, Di * B * C);
-  resize_bwd_kernel<<<grid, block, 0, as_stream(stream)>>>(grad_out, grad_x, g);
+  auto fits = [](const AxisMap& m) { return m.in == m.out || (m.ratio > 0.f && 2.0f / m.ratio + 5.0f <= (float)ADJ_MAX + 2.f); };
+  if (fits(g.mz) && fits(g.my) && fits(g.mx)) resize_bwd_table_kernel<<<grid, block, 0, as_stream(stream)>>>(grad_out, grad_x, g);
+  else resize_bwd_kernel<<<grid, block, 0, as_stream(stream)>>>(grad_out, grad_x, g);
   return check_launch("resize_bwd");
 }

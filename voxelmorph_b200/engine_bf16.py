@@ -93,8 +93,8 @@ def forward_tape(model, source, target):
     _lib.require_cuda(source, target, what="VxmDense")
     source, target = _lib.contig(source), _lib.contig(target)
     planes = [source[:, i:i + 1] for i in range(source.shape[1])] + [target[:, i:i + 1] for i in range(target.shape[1])]
-    if len(planes) > 4:
-        raise _lib.VxmError("bf16 engine: at most 4 input feature planes (src_feats + trg_feats)")
+    if len(planes) > 8:
+        raise _lib.VxmError("bf16 engine: at most 8 input feature planes (src_feats + trg_feats)")
     tape = []            # list of ("conv", _Conv) / ("pool", in_id, out_id)
     tensors = {}         # id -> bf16 NDHWC tensor
     producer = {}        # id -> "conv" | "pool"
@@ -118,7 +118,11 @@ def forward_tape(model, source, target):
         if planar is None:
             ca = 0 if cv.xa is None else cv.xa.shape[-1]
             cb = 0 if cv.xb is None else cv.xb.shape[-1]
-            if ca + cb != cv.cin or (ca + cb) % 16 or ca + cb > 64:
+            first_layer = cv.xa is not None and producer.get(a_id) == "input"
+            if first_layer:
+                if ca != 8 or cb or cv.cin > 8:
+                    raise _lib.VxmError("bf16 engine: the first convolution takes at most 8 input feature planes")
+            elif ca + cb != cv.cin or (ca + cb) % 16 or ca + cb > 64:
                 raise _lib.VxmError("bf16 engine: unsupported convolution input channels %d (+%d); need a multiple of 16, at most 64"
                                     % (ca, cb))
         out = _run_conv(cv, kd)
@@ -138,17 +142,15 @@ def forward_tape(model, source, target):
         tape.append(("pool", in_id, oid))
         return oid
 
-    cur = None           # current tensor id (None = the raw planar input)
+    # the fp32 images enter as one bf16 channels-last tensor with 8 channels (src planes, trg planes, zeros)
+    cur = new_id()
+    tensors[cur] = tc.planar_to_ndhwc8(planes)
+    producer[cur] = "input"
     skips = [None]
-    first = True
     for level, convs in enumerate(unet.encoder):
         for blk in convs:
             slope = blk.activation.negative_slope
-            if first:
-                cur = conv(blk.main, slope, planar=planes)
-                first = False
-            else:
-                cur = conv(blk.main, slope, a_id=cur)
+            cur = conv(blk.main, slope, a_id=cur)
         skips.append(cur)
         cur = pool(cur)
     pending_up = None    # (a_id, skip_id) to be consumed by the next convolution as a fused upsample+concat
@@ -200,23 +202,17 @@ def backward_tape(ctx, g_flow):
             continue
         cv = entry[1]
         if cv.planar_out:
-            g_planes = [g_flow[:, i:i + 1] for i in range(g_flow.shape[1])]
-            gw, _ = tc.conv_wgrad(cv.xa, cv.xb, None, cv.cin, cv.cout, kd, up=cv.up, planar_g=g_planes, need_bias=False)
-            gb = torch.empty(cv.cout, dtype=torch.float32, device=dev)
-            work = torch.empty(128 * cv.cout, dtype=torch.float32, device=dev)
-            V = g_flow[0, 0].numel()
-            _lib.check(lib.vxm_planar_channel_sums(_lib.ptr(g_flow), _lib.ptr(gb), _lib.ptr(work), g_flow.shape[0], cv.cout, V,
-                                                   _lib.stream_ptr()), "vxm_planar_channel_sums")
-            g_in_planar, g_in = g_planes, None
+            # flow head: the fp32 planar flow gradient becomes an 8-channel bf16 channels-last tensor
+            g_in = tc.planar_to_ndhwc8([g_flow[:, i:i + 1] for i in range(g_flow.shape[1])])
         else:
             g_in = gz.pop(cv.out_id)
-            gw, gb = tc.conv_wgrad(cv.xa, cv.xb, g_in, cv.cin, cv.cout, kd, up=cv.up, planar_x=cv.planar)
-            g_in_planar = None
+        gw, gb = tc.conv_wgrad(cv.xa, cv.xb, g_in, cv.cin, cv.cout, kd, up=cv.up, planar_x=cv.planar)
+        g_in_planar = None
         grads[cv.w] = gw.squeeze(2) if nd == 2 else gw
         if cv.b is not None:
             grads[cv.b] = gb
         # ---- dgrad ----
-        if cv.planar is not None:
+        if cv.planar is not None or producer.get(cv.a_id) == "input":
             continue       # first layer: the images need no gradient
         w = cv.w.detach()
         if cv.b_id is None:

@@ -103,7 +103,7 @@ def conv_wgrad(xa, xb, gz, cin, cout, kd, up=False, planar_x=None, planar_g=None
         work = torch.empty(int(lib.vxm_conv3d_tc_wgrad_workspace_bytes(kd)), dtype=torch.uint8, device=dev)
         _wgrad_ws[key] = work
     gw = torch.empty((cout, cin, kd, 3, 3), dtype=torch.float32, device=dev)
-    gb = torch.empty(cout, dtype=torch.float32, device=dev) if (need_bias and planar_g is None) else None
+    gb = torch.empty(cout, dtype=torch.float32, device=dev) if need_bias else None
     xf, xs, npx = _planar_args(planar_x)
     gf, gs, npg = _planar_args(planar_g)
     Ca = 0 if xa is None else xa.shape[-1]
@@ -112,3 +112,18 @@ def conv_wgrad(xa, xb, gz, cin, cout, kd, up=False, planar_x=None, planar_g=None
                                        _lib.ptr(gb), _lib.ptr(work), B, D, H, W, Ca, Cb, 1 if up else 0, cin, Cg, cout, kd,
                                        _lib.stream_ptr()), "vxm_conv3d_tc_wgrad")
     return gw, gb
+
+
+def planar_to_ndhwc8(planes):
+    """<= 8 planar fp32 (B,1,[D,]H,W) volumes -> one bf16 (B,D,H,W,8) tensor (unused channels zero)."""
+    lib = _lib.load()
+    ref = planes[0]
+    B = ref.shape[0]
+    D, H, W = (ref.shape[-3] if ref.dim() == 5 else 1), ref.shape[-2], ref.shape[-1]
+    n = len(planes)
+    arr_p = (ctypes.c_void_p * 8)(*([p.data_ptr() for p in planes] + [0] * (8 - n)))
+    arr_s = (ctypes.c_longlong * 8)(*([p.stride(0) for p in planes] + [0] * (8 - n)))
+    out = torch.empty((B, D, H, W, 8), dtype=torch.bfloat16, device=ref.device)
+    _lib.check(lib.vxm_planar_to_ndhwc8_bf16(arr_p, arr_s, n, _lib.ptr(out), B, D * H * W, _lib.stream_ptr()),
+               "vxm_planar_to_ndhwc8_bf16")
+    return out
