@@ -1,0 +1,55 @@
+"""Live pin of the oracle restatements against the UNMODIFIED reference imported from /root/reference (build container
+only; skipped on the GPU box where the reference tree does not exist)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases, ref_import, ref_torch, spec_np
+
+pytestmark = pytest.mark.skipif(not ref_import.available(), reason="reference tree not present")
+
+
+def t(x):
+    return torch.from_numpy(np.ascontiguousarray(x))
+
+
+@pytest.fixture(scope="module")
+def vxm_ref():
+    return ref_import.import_reference()
+
+
+def test_layers_live(vxm_ref):
+    shape = (10, 14, 12)
+    src = cases.smooth_volume(1, shape)
+    flow = cases.smooth_field(2, 3, shape, scale=5.0)
+    lab = cases.label_volume(3, shape)
+    assert np.array_equal(vxm_ref.layers.SpatialTransformer(shape)(t(src), t(flow)).numpy(), spec_np.warp(src, flow))
+    assert np.array_equal(vxm_ref.layers.SpatialTransformer(shape, mode="nearest")(t(lab), t(flow)).numpy(),
+                          spec_np.warp(lab, flow, mode="nearest"))
+    assert np.array_equal(vxm_ref.layers.VecInt(shape, 5)(t(flow)).numpy(), spec_np.vecint(flow, 5))
+    for vr in (2, 0.5):
+        r = vxm_ref.layers.ResizeTransform(vr, 3)(t(flow))
+        assert np.array_equal(r.numpy(), ref_torch.resize_transform(t(flow), vr).numpy())
+        np.testing.assert_allclose(spec_np.resize_flow(flow, vr), r.numpy(), rtol=0, atol=5e-6 * np.abs(flow).max())
+
+
+def test_losses_live(vxm_ref):
+    NCC = ref_import.reference_ncc_class(vxm_ref)
+    I, J = cases.volume_pair(7, (16, 20, 18))
+    assert abs(NCC().loss(t(I), t(J)).item() - spec_np.ncc_loss(I, J)) < 2e-6
+    assert NCC().loss(t(I), t(J)).item() == ref_torch.ncc_loss(t(I), t(J)).item()
+    f = cases.smooth_field(8, 3, (8, 10, 12), scale=2.0)
+    assert abs(vxm_ref.losses.Grad("l2", loss_mult=2).loss(None, t(f)).item() - spec_np.grad_loss(f, "l2", 2)) < 1e-6
+    assert abs(vxm_ref.losses.MSE().loss(t(I), t(J)).item() - spec_np.mse_loss(I, J)) < 1e-7
+
+
+def test_network_live(vxm_ref):
+    kw = dict(inshape=(16, 16, 32), nb_unet_features=[[4, 8, 8, 8], [8, 8, 8, 8, 8, 4, 4]], bidir=True)
+    m = vxm_ref.networks.VxmDense(**kw)
+    sd = ref_torch.init_state_dict(m.config, seed=5, flow_std=2e-2)
+    m.load_state_dict(sd, strict=False)
+    s, g = cases.volume_pair(9, kw["inshape"])
+    with torch.no_grad():
+        a = m(t(s), t(g))
+        b = ref_torch.vxm_forward(sd, m.config, t(s), t(g))
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
