@@ -304,9 +304,6 @@ def b200_arm(args):
                ms_per_step=ms_e2e / K, api="voxelmorph_b200.networks.VxmDense + losses.NCC/Grad + optim.FusedAdam, pinned host "
                "buffers, H2D double-buffered on a copy stream")
 
-    if rank != 0:
-        return
-
     # ---- roofline of the dominant kernel family (Conv3d) measured live with CUDA events -------------
     from voxelmorph_b200 import ops
     conv_ms = []
@@ -335,6 +332,10 @@ def b200_arm(args):
     torch.cuda.synchronize()
     ops._ConvK3Fn.forward, ops._ConvK3Fn.backward = staticmethod(orig_fwd), staticmethod(orig_bwd)
     tcmod.conv_fwd, tcmod.conv_wgrad = o_cf, o_cw
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
     conv_total_ms = sum(a.elapsed_time(b) for a, b in conv_ms) / NPROF
     _, flops_step = conv_flops_per_step(shape)
     ach = flops_step / (conv_total_ms * 1e-3) / 1e12
@@ -366,6 +367,8 @@ def b200_arm(args):
                 clocks=clk, e2e=e2e, gpu_launches=int(launches), launches_per_step=launches / K,
                 roofline=roofline, kernels=kernels, cpu_baseline=cpu)
     print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
 
 
 def kernel_rooflines(vxm, dev, shape, peaks):
