@@ -32,6 +32,7 @@ def parse():
     ap.add_argument("--shape", type=int, nargs=3, default=list(FULL), help="debug only; the metric is quoted at 160 192 224")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--engine", default=None, choices=["f32", "bf16"], help="convolution engine (default: bf16 tensor-core engine)")
+    ap.add_argument("--no-graph", action="store_true", help="time eager kernel launches instead of the captured CUDA graph")
     ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline legs")
     return ap.parse_args()
 
@@ -232,7 +233,7 @@ def b200_arm(args):
     pairs_dev = [(s.to(dev), t.to(dev)) for s, t in pairs_host]
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
 
-    def step(S, T):
+    def eager_step(S, T):
         opt.zero_grad()
         y, flow = model(S, T)
         loss = ncc(T, y) + 0.01 * grad(None, flow)
@@ -240,6 +241,20 @@ def b200_arm(args):
         vdist.allreduce_grads(opt.fp.grad)
         opt.step()
         return loss
+
+    # the whole step (zero-grad, fwd, losses, bwd, allreduce, Adam) captured once in a CUDA graph and replayed
+    step, graphed = eager_step, False
+    launches_per_step = None
+    if not args.no_graph:
+        from voxelmorph_b200.trainer import GraphedTrainStep
+        try:
+            n0 = vxm._lib.launch_count()
+            eager_step(*pairs_dev[0])
+            launches_per_step = vxm._lib.launch_count() - n0
+            trainer = GraphedTrainStep(model, opt, image_loss="ncc", lam=0.01, int_downsize=2).capture(*pairs_dev[0])
+            step, graphed = trainer, True
+        except Exception as e:  # noqa: BLE001 - report and fall back to eager launches
+            print("bench.py: CUDA graph capture failed (%s); timing eager launches" % e, file=sys.stderr)
 
     def barrier():
         if world > 1:
@@ -265,7 +280,7 @@ def b200_arm(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = vxm._lib.launch_count() - n0
+    launches = (launches_per_step * K) if graphed else (vxm._lib.launch_count() - n0)
     ms = vdist.max_over_ranks(ms, dev)
     clk = clocks.stop() if rank == 0 else None
     value = world * K / (ms * 1e-3)
@@ -328,7 +343,7 @@ def b200_arm(args):
         ops._ConvK3Fn.backward = staticmethod(timed(orig_bwd))
     NPROF = 2
     for i in range(NPROF):
-        step(*pairs_dev[i % NPAIR])
+        eager_step(*pairs_dev[i % NPAIR])
     torch.cuda.synchronize()
     ops._ConvK3Fn.forward, ops._ConvK3Fn.backward = staticmethod(orig_fwd), staticmethod(orig_bwd)
     tcmod.conv_fwd, tcmod.conv_wgrad = o_cf, o_cw
@@ -361,7 +376,7 @@ def b200_arm(args):
                 config=dict(workload="3D %s VxmDense diffeomorphic (int_steps=7, int_downsize=2), default U-Net features, "
                             "NCC(9^3)+0.01*Grad(l2), Adam lr 1e-4, 1 pair per GPU" % "x".join(map(str, shape)),
                             global_batch=world, parallelism="dp%d (one flat-gradient allreduce per step)" % world,
-                            conv_engine=engine,
+                            conv_engine=engine, cuda_graph=graphed,
                             l2="inputs rotate over %d resident pairs; per-step working set ~%.1f GB of full-resolution "
                                "activations >> 126 MB L2, so no explicit flush" % (NPAIR, act_gb)),
                 clocks=clk, e2e=e2e, gpu_launches=int(launches), launches_per_step=launches / K,

@@ -202,6 +202,10 @@ int vxm_adam_step(float* p, const float* g, float* m, float* v, size_t n, int st
                   float beta1, float beta2, float eps, float weight_decay, float grad_scale,
                   void* stream);
 
+/* Same update with the step count kept on the device (incremented by the call): safe to capture in a CUDA graph. */
+int vxm_adam_step_dev(float* p, const float* g, float* m, float* v, size_t n, int* step_counter, float lr,
+                      float beta1, float beta2, float eps, float weight_decay, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

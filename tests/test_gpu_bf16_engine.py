@@ -113,3 +113,37 @@ def test_bf16_engine_rejects_unsupported_shapes(vxm_bf16, cuda):
     m = vxm.networks.VxmDense((16, 16, 16), nb_unet_features=[[4, 8, 8, 8], [8, 8, 8, 8, 8, 4, 4]]).to(cuda)
     with pytest.raises(vxm._lib.VxmError, match="VXM_B200_CONV_ENGINE=f32"):
         m(torch.rand(1, 1, 16, 16, 16, device=cuda), torch.rand(1, 1, 16, 16, 16, device=cuda))
+
+
+def test_graphed_train_step_matches_eager(vxm_bf16, cuda):
+    """The CUDA-graph replay of the whole step produces the same loss sequence / parameters as eager launches."""
+    vxm = vxm_bf16
+    from voxelmorph_b200.trainer import GraphedTrainStep
+    kw = dict(inshape=(32, 32, 32))
+    cfg = full_cfg(kw)
+    s, tr = cases.volume_pair(95, kw["inshape"], sigma=1.5)
+    S, T = t(s).to(cuda), t(tr).to(cuda)
+
+    def make():
+        m = vxm.networks.VxmDense(**kw)
+        m.load_state_dict(ref_torch.init_state_dict(cfg, seed=5, flow_std=2e-2), strict=False)
+        m.to(cuda).train()
+        return m, vxm.optim.FusedAdam(m.parameters(), lr=1e-3)
+
+    m1, o1 = make()
+    eager = []
+    for _ in range(6):
+        o1.zero_grad()
+        y, flow = m1(S, T)
+        loss = vxm.losses.NCC().loss(T, y) + 0.01 * vxm.losses.Grad("l2", loss_mult=2).loss(None, flow)
+        loss.backward()
+        o1.step()
+        eager.append(float(loss))
+    m2, o2 = make()
+    tr2 = GraphedTrainStep(m2, o2, warmup=3).capture(S, T)      # 3 eager warm-up steps; capture itself executes nothing
+    graphed = [float(tr2(S, T)) for _ in range(3)]
+    # replays are steps 4, 5, 6 of the trajectory (atomics in the VecInt / warp backward make the two runs agree only
+    # to rounding)
+    for i in range(3):
+        assert abs(graphed[i] - eager[3 + i]) <= 2e-3 * abs(eager[3 + i]), (i, graphed, eager)
+    assert int(o2.step_dev.item()) == 6

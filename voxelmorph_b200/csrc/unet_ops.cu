@@ -114,6 +114,25 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
 }
 
+// Graph-friendly variant: the step count lives on the device (the bias corrections cannot be baked into a captured graph).
+__global__ void __launch_bounds__(256) adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                       float* __restrict__ v, size_t n, const int* __restrict__ step_ptr, float lr, float b1,
+                                                       float b2, float eps, float wd, float gscale) {
+  const int step = *step_ptr;
+  const float lr_c = (float)((double)lr / (1.0 - pow((double)b1, (double)step)));
+  const float inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)b2, (double)step)));
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * gscale, pi = p[i];
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+    p[i] = pi - lr_c * (mi / denom);
+  }
+}
+__global__ void increment_kernel(int* c) { *c += 1; }
+
 static int ew_grid(size_t n) {
   size_t b = (n + 1023) / 1024;
   size_t cap = (size_t)sm_count() * 16;
@@ -197,4 +216,14 @@ extern "C" int vxm_adam_step(float* p, const float* g, float* m, float* v, size_
   adam_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(p, g, m, v, n, lr_c, inv_sqrt_bc2, beta1, beta2, eps,
                                                          weight_decay, grad_scale);
   return check_launch("adam_step");
+}
+
+extern "C" int vxm_adam_step_dev(float* p, const float* g, float* m, float* v, size_t n, int* step_counter, float lr, float beta1,
+                                 float beta2, float eps, float weight_decay, float grad_scale, void* stream) {
+  VXM_REQUIRE(p && g && m && v && n > 0 && step_counter, "adam_step_dev: bad argument");
+  increment_kernel<<<1, 1, 0, as_stream(stream)>>>(step_counter);
+  int rc = check_launch("adam_increment");
+  if (rc) return rc;
+  adam_dev_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(p, g, m, v, n, step_counter, lr, beta1, beta2, eps, weight_decay, grad_scale);
+  return check_launch("adam_step_dev");
 }

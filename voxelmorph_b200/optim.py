@@ -52,6 +52,7 @@ class FusedAdam:
         self.m = torch.zeros_like(self.fp.flat)
         self.v = torch.zeros_like(self.fp.flat)
         self.step_count = 0
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.fp.flat.device)   # device-side step count (graph capture)
         self.grad_scale = 1.0 / world_size
 
     def zero_grad(self, set_to_none=False):
@@ -69,8 +70,8 @@ class FusedAdam:
                 p.grad = g.view_as(p)
             off += k
         lib = _lib.load()
-        _lib.check(lib.vxm_adam_step(_lib.ptr(self.fp.flat), _lib.ptr(self.fp.grad), _lib.ptr(self.m), _lib.ptr(self.v),
-                                     self.fp.numel, self.step_count, self.lr, self.betas[0], self.betas[1], self.eps,
-                                     self.weight_decay, self.grad_scale, _lib.stream_ptr()), "vxm_adam_step")
+        _lib.check(lib.vxm_adam_step_dev(_lib.ptr(self.fp.flat), _lib.ptr(self.fp.grad), _lib.ptr(self.m), _lib.ptr(self.v),
+                                         self.fp.numel, _lib.ptr(self.step_dev), self.lr, self.betas[0], self.betas[1], self.eps,
+                                         self.weight_decay, self.grad_scale, _lib.stream_ptr()), "vxm_adam_step_dev")
         from . import engine_bf16
         engine_bf16.bump_weights_epoch()   # parameters changed behind torch's version counter
