@@ -320,44 +320,70 @@ def b200_arm(args):
                "buffers, H2D double-buffered on a copy stream")
 
     # ---- roofline of the dominant kernel family (Conv3d) measured live with CUDA events -------------
+    # One eager step records every convolution launch (function + arguments); the recorded launches are then
+    # re-issued back to back between two CUDA events on the launching stream, behind a device-side sleep so that the
+    # host runs ahead and the events bracket kernel time only (no launch gaps).
     from voxelmorph_b200 import ops
-    conv_ms = []
-    orig_fwd, orig_bwd = ops._ConvK3Fn.forward, ops._ConvK3Fn.backward
+    from voxelmorph_b200 import tc as tcmod
+    calls = []
 
-    def timed(fn):
+    def recording(fn):
         def inner(*a, **k):
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record()
-            r = fn(*a, **k)
-            a1.record()
-            conv_ms.append((a0, a1))
-            return r
+            calls.append((fn, a, k))
+            return fn(*a, **k)
         return inner
 
-    from voxelmorph_b200 import tc as tcmod
     o_cf, o_cw = tcmod.conv_fwd, tcmod.conv_wgrad
+    orig_fwd, orig_bwd = ops._ConvK3Fn.forward, ops._ConvK3Fn.backward
+    conv_total_ms = None
     if ops.conv_engine() == "bf16":
-        tcmod.conv_fwd, tcmod.conv_wgrad = timed(o_cf), timed(o_cw)
+        tcmod.conv_fwd, tcmod.conv_wgrad = recording(o_cf), recording(o_cw)
+        eager_step(*pairs_dev[0])
+        tcmod.conv_fwd, tcmod.conv_wgrad = o_cf, o_cw
+        torch.cuda.synchronize()
+        reps = []
+        for _ in range(3):
+            torch.cuda._sleep(12000000)
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for fn, a, k in calls:
+                fn(*a, **k)
+            c1.record()
+            torch.cuda.synchronize()
+            reps.append(c0.elapsed_time(c1))
+        conv_total_ms = statistics.median(reps)
+        n_conv_launches = len(calls)
+        del calls
     else:
+        conv_ms = []
+
+        def timed(fn):
+            def inner(*a, **k):
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                r = fn(*a, **k)
+                a1.record()
+                conv_ms.append((a0, a1))
+                return r
+            return inner
+
         ops._ConvK3Fn.forward = staticmethod(timed(orig_fwd))
         ops._ConvK3Fn.backward = staticmethod(timed(orig_bwd))
-    NPROF = 2
-    for i in range(NPROF):
-        eager_step(*pairs_dev[i % NPAIR])
-    torch.cuda.synchronize()
-    ops._ConvK3Fn.forward, ops._ConvK3Fn.backward = staticmethod(orig_fwd), staticmethod(orig_bwd)
-    tcmod.conv_fwd, tcmod.conv_wgrad = o_cf, o_cw
+        eager_step(*pairs_dev[0])
+        torch.cuda.synchronize()
+        ops._ConvK3Fn.forward, ops._ConvK3Fn.backward = staticmethod(orig_fwd), staticmethod(orig_bwd)
+        conv_total_ms = sum(x.elapsed_time(y) for x, y in conv_ms)
+        n_conv_launches = len(conv_ms)
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
         return
-    conv_total_ms = sum(a.elapsed_time(b) for a, b in conv_ms) / NPROF
     _, flops_step = conv_flops_per_step(shape)
     ach = flops_step / (conv_total_ms * 1e-3) / 1e12
     engine = ops.conv_engine()
     roofline = dict(bound="tensor", kernel="conv3d k3 fwd+dgrad+wgrad, all 12 layers (%s)" % ("tcgen05 bf16 implicit GEMM" if engine == "bf16" else "fp32 FFMA engine"),
                     achieved=ach, peak=peaks["tf_sus"], unit="TFLOP/s", frac=ach / peaks["tf_sus"], traffic=None,
-                    peak_source=peaks["source"] + ", sustained bf16", ms_per_step=conv_total_ms,
+                    peak_source=peaks["source"] + ", sustained bf16", ms_per_step=conv_total_ms, conv_launches=n_conv_launches,
                     share_of_step=conv_total_ms / (ms / K), flops_per_step=flops_step)
 
     kernels = {} if args.no_kernels else kernel_rooflines(vxm, dev, shape, peaks)
@@ -417,12 +443,17 @@ def kernel_rooflines(vxm, dev, shape, peaks):
 
     with torch.no_grad():
         src = torch.rand((1, 1) + shape, device=dev)
-        flow = torch.randn((1, 3) + shape, device=dev) * 3.0
+        smooth = lambda shp, sig: (torch.nn.functional.interpolate(  # noqa: E731  registration-like smooth displacement field
+            torch.randn((1, 3) + tuple(max(2, s // 16) for s in shp), device=dev) * sig, size=shp, mode="trilinear",
+            align_corners=True).contiguous())
+        flow = smooth(shape, 3.0)
+        rough = torch.randn((1, 3) + shape, device=dev) * 3.0
         st = vxm.layers.SpatialTransformer(shape)
         stn = vxm.layers.SpatialTransformer(shape, mode="nearest")
-        timeit(lambda: st(src, flow), V * 20, "warp_fwd_linear", "C=1, sigma=3 voxels")
-        timeit(lambda: stn(src, flow), V * 20, "warp_fwd_nearest", "C=1")
-        vel = torch.randn((1, 3) + half, device=dev) * 2.0
+        timeit(lambda: st(src, flow), V * 20, "warp_fwd_linear", "C=1, smooth flow sigma=3 voxels (registration-like)")
+        timeit(lambda: stn(src, flow), V * 20, "warp_fwd_nearest", "C=1, smooth flow")
+        timeit(lambda: st(src, rough), V * 20, "warp_fwd_linear_white_noise_flow", "C=1, i.i.d. N(0,3^2) flow per voxel (worst-case gather locality)")
+        vel = smooth(half, 2.0)
         vi = vxm.layers.VecInt(half, 7)
         timeit(lambda: vi(vel), Vh * 24 * 7, "vecint_fwd_7steps", "single cooperative launch; field is L2 resident, so frac can "
                "exceed 1 against the HBM peak")

@@ -153,7 +153,9 @@ int vxm_conv3d_tc_pack(const float* w, void* wpk, int Cout, int Cin, int kd, int
 int vxm_conv3d_tc_fwd(const void* xa, const void* xb, const float* const* xf, const long long* xf_bstride,
                       int nplanar, const void* wpk, const float* bias, void* out, const void* mask,
                       int B, int D, int H, int W, int Ca, int Cb, int up, int Cout, int np, int kd,
-                      int out_mode, float slope, void* stream);
+                      int out_mode, float slope, void* out2, int csplit, void* stream);
+/* out2 != NULL (bf16 outputs only): channels [0,csplit) go to `out` (B,D,H,W,csplit) and [csplit,Cout) to `out2`
+ * (B,D,H,W,Cout-csplit) — the single-pass dgrad of a layer whose input was a channel concat; np may then be 48 or 64. */
 /* Weight (and bias) gradient on tensor cores.  x sources as in vxm_conv3d_tc_fwd (the layer's forward input);
  * gz = gradient w.r.t. the convolution output (already multiplied by the activation derivative): bf16 NDHWC with
  * Cg in {8,16,32} channels, or nplanar_g (<= 4) planar fp32 volumes (flow head).  grad_w: fp32

@@ -101,6 +101,22 @@ def test_tc_dgrad_with_mask(tc, cuda):
     assert rel_err(tc.from_ndhwc(out).cpu(), ref) <= 1e-2
 
 
+@pytest.mark.parametrize("Cin,split", [(48, 32), (64, 32)])
+def test_tc_dgrad_split_outputs(tc, cuda, Cin, split):
+    """Single-pass dgrad of a concat layer: N = Cin (48 / 64) output channels written to two tensors."""
+    g = torch.Generator().manual_seed(8)
+    Cout, shape = 32, (6, 16, 24)
+    x = torch.randn((1, Cin) + shape, generator=g, dtype=torch.float64, requires_grad=True)
+    w = bf(torch.randn((Cout, Cin, 3, 3, 3), generator=g) * 0.1)
+    gy = bf(torch.randn((1, Cout) + shape, generator=g))
+    F.conv3d(x, w.double(), None, padding=1).backward(gy.double())
+    wpk, NP = tc.pack_weights(w.to(cuda), transposed=True)
+    assert NP == Cin
+    oa, ob = tc.conv_fwd(tc.to_ndhwc_bf16(gy.to(cuda)), None, wpk, NP, None, Cin, 3, split=split)
+    assert rel_err(tc.from_ndhwc(oa).cpu(), x.grad[:, :split]) <= 1e-2
+    assert rel_err(tc.from_ndhwc(ob).cpu(), x.grad[:, split:]) <= 1e-2
+
+
 WG_CASES = [
     # shape, Ca, Cb, up, Cout
     ((4, 16, 8), 16, 0, False, 16),

@@ -42,6 +42,8 @@ struct ConvTcArgs {
   const __nv_bfloat16* wpk;   // packed weights
   const float* bias;
   void* out;
+  void* out2;                 // optional second bf16 NDHWC output: channels [csplit, Cout) go there (dgrad of a concat layer)
+  int csplit;
   const __nv_bfloat16* mask;  // optional bf16 NDHWC (B,D,H,W,Cout): out *= (mask < 0 ? slope : 1), no activation
   int B, D, H, W;
   int Ca, Cb, up, upd;
@@ -76,6 +78,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const ConvTcArgs a
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t tmem_cols = (NACC * NP <= 32) ? 32u : ((NACC * NP <= 64) ? 64u : 128u);
+  static_assert(NACC * NP <= 128, "accumulators exceed the TMEM allocation");
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSLOT; ++i) { mbar_init(&full[i], NLOADER); mbar_init(&empty[i], 1); }
@@ -268,6 +271,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const ConvTcArgs a
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * (uint32_t)NP;
         tmem_ld16(taddr, r);
         if constexpr (NP > 16) tmem_ld16(taddr + 16, r + 16);
+        if constexpr (NP > 32) tmem_ld16(taddr + 32, r + 32);
+        if constexpr (NP > 48) tmem_ld16(taddr + 48, r + 48);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&tempty[acc]);
@@ -275,7 +280,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const ConvTcArgs a
         if (!inside) continue;
         const size_t vox = (((size_t)b * a.D + d) * a.H + h) * a.W + w;
         if (a.out_mode == 0) {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + vox * a.Cout;
+          const int c1 = a.out2 ? a.csplit : a.Cout;          // channels [0,c1) -> out, [c1,Cout) -> out2
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + vox * c1;
+          __nv_bfloat16* o2 = a.out2 ? reinterpret_cast<__nv_bfloat16*>(a.out2) + vox * (a.Cout - c1) - c1 : nullptr;
           const __nv_bfloat16* mk = a.mask ? a.mask + vox * a.Cout : nullptr;
 #pragma unroll
           for (int c0 = 0; c0 < NP; c0 += 8) {
@@ -297,7 +304,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const ConvTcArgs a
                 for (int e = 0; e < 8; ++e) v[e] = v[e] >= 0.f ? v[e] : v[e] * a.slope;
               }
               uint4 q = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-              *reinterpret_cast<uint4*>(o + c0) = q;
+              *reinterpret_cast<uint4*>((c0 < c1 ? o : o2) + c0) = q;
             }
           }
         } else {
@@ -350,7 +357,7 @@ extern "C" size_t vxm_conv3d_tc_packed_bytes(int cin_eff, int np, int kd) {
 }
 
 extern "C" int vxm_conv3d_tc_pack(const float* w, void* wpk, int Cout, int Cin, int kd, int np, int transposed, void* stream) {
-  VXM_REQUIRE(w && wpk && Cout > 0 && Cin > 0 && (kd == 1 || kd == 3) && np % 16 == 0 && np <= 32, "conv3d_tc_pack: bad argument");
+  VXM_REQUIRE(w && wpk && Cout > 0 && Cin > 0 && (kd == 1 || kd == 3) && np % 16 == 0 && np <= 64, "conv3d_tc_pack: bad argument");
   int cin_eff = transposed ? Cout : Cin, nout = transposed ? Cin : Cout;
   VXM_REQUIRE(nout <= np, "conv3d_tc_pack: %d output channels do not fit N=%d", nout, np);
   int K16 = (cin_eff + 15) / 16, T = kd * 9;
@@ -361,10 +368,11 @@ extern "C" int vxm_conv3d_tc_pack(const float* w, void* wpk, int Cout, int Cin, 
 
 extern "C" int vxm_conv3d_tc_fwd(const void* xa, const void* xb, const float* const* xf, const long long* xf_bstride, int nplanar,
                                  const void* wpk, const float* bias, void* out, const void* mask, int B, int D, int H, int W,
-                                 int Ca, int Cb, int up, int Cout, int np, int kd, int out_mode, float slope, void* stream) {
+                                 int Ca, int Cb, int up, int Cout, int np, int kd, int out_mode, float slope, void* out2, int csplit,
+                                 void* stream) {
   VXM_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && wpk && out, "conv3d_tc_fwd: bad argument");
   VXM_REQUIRE(kd == 1 || kd == 3, "conv3d_tc_fwd: kd must be 1 or 3");
-  VXM_REQUIRE(np == 16 || np == 32, "conv3d_tc_fwd: N must be 16 or 32");
+  VXM_REQUIRE(np == 16 || np == 32 || np == 48 || np == 64, "conv3d_tc_fwd: N must be 16, 32, 48 or 64");
   VXM_REQUIRE(Cout > 0 && Cout <= np && (out_mode == 1 || Cout % 8 == 0), "conv3d_tc_fwd: unsupported Cout %d", Cout);
   ConvTcArgs a{};
   int Cin;
@@ -383,6 +391,8 @@ extern "C" int vxm_conv3d_tc_fwd(const void* xa, const void* xb, const float* co
   }
   a.xa = (const __nv_bfloat16*)xa; a.xb = (const __nv_bfloat16*)xb; a.wpk = (const __nv_bfloat16*)wpk; a.bias = bias;
   a.out = out; a.mask = (const __nv_bfloat16*)mask;
+  a.out2 = out2; a.csplit = csplit;
+  VXM_REQUIRE(!out2 || (out_mode == 0 && csplit > 0 && csplit < Cout && csplit % 8 == 0 && !mask), "conv3d_tc_fwd: bad output split");
   a.B = B; a.D = D; a.H = H; a.W = W; a.Ca = Ca; a.Cb = Cb; a.up = up; a.upd = (up && kd == 3) ? 1 : 0;
   a.Cout = Cout; a.NP = np; a.KD = kd; a.out_mode = out_mode; a.slope = slope;
   a.tiles_h = (H + TH - 1) / TH; a.tiles_w = (W + TW - 1) / TW;
@@ -418,7 +428,7 @@ extern "C" int vxm_conv3d_tc_fwd(const void* xa, const void* xb, const float* co
     case 3: VXM_TC_LAUNCH(KD_, 3, NP_); break;                                 \
     default: VXM_TC_LAUNCH(KD_, 4, NP_); break;                                \
   }
-  if (kd == 3) { if (np == 16) { VXM_TC_NK(3, 16) } else { VXM_TC_NK(3, 32) } }
-  else { if (np == 16) { VXM_TC_NK(1, 16) } else { VXM_TC_NK(1, 32) } }
+  if (kd == 3) { if (np == 16) { VXM_TC_NK(3, 16) } else if (np == 32) { VXM_TC_NK(3, 32) } else if (np == 48) { VXM_TC_NK(3, 48) } else { VXM_TC_NK(3, 64) } }
+  else { if (np == 16) { VXM_TC_NK(1, 16) } else if (np == 32) { VXM_TC_NK(1, 32) } else if (np == 48) { VXM_TC_NK(1, 48) } else { VXM_TC_NK(1, 64) } }
   return check_launch("conv3d_tc_fwd");
 }

@@ -103,6 +103,53 @@ __device__ __forceinline__ float sample_linear(const float* __restrict__ plane, 
   return acc;
 }
 
+// Branch-free form of the same stencil for the hot forward kernels: 32-bit clamped offsets and weights that are
+// exactly 0 for out-of-volume corners.  acc + v*0 leaves acc unchanged, so the result equals the predicated form
+// (for finite inputs) bit for bit, with ~3x fewer instructions.
+struct Stencil8 {
+  int off[8];
+  float w[8];
+};
+template <bool IS3D>
+__device__ __forceinline__ void make_stencil8(float cx, float cy, float cz, int D, int H, int W, Stencil8& s) {
+  const float fx = floorf(cx), fy = floorf(cy);
+  const int x0 = f2i(fx), y0 = f2i(fy);
+  float wx0 = __fsub_rn(__fadd_rn(fx, 1.0f), cx), wx1 = __fsub_rn(cx, fx);
+  float wy0 = __fsub_rn(__fadd_rn(fy, 1.0f), cy), wy1 = __fsub_rn(cy, fy);
+  wx0 = (unsigned)x0 < (unsigned)W ? wx0 : 0.f;
+  wx1 = (unsigned)(x0 + 1) < (unsigned)W ? wx1 : 0.f;
+  wy0 = (unsigned)y0 < (unsigned)H ? wy0 : 0.f;
+  wy1 = (unsigned)(y0 + 1) < (unsigned)H ? wy1 : 0.f;
+  const int xa = min(max(x0, 0), W - 1), xb = min(max(x0, -1) + 1, W - 1);
+  const int ya = min(max(y0, 0), H - 1) * W, yb = (min(max(y0, -1) + 1, H - 1)) * W;
+  const float w00 = __fmul_rn(wx0, wy0), w10 = __fmul_rn(wx1, wy0), w01 = __fmul_rn(wx0, wy1), w11 = __fmul_rn(wx1, wy1);
+  if (IS3D) {
+    const float fz = floorf(cz);
+    const int z0 = f2i(fz);
+    float wz0 = __fsub_rn(__fadd_rn(fz, 1.0f), cz), wz1 = __fsub_rn(cz, fz);
+    wz0 = (unsigned)z0 < (unsigned)D ? wz0 : 0.f;
+    wz1 = (unsigned)(z0 + 1) < (unsigned)D ? wz1 : 0.f;
+    const int za = min(max(z0, 0), D - 1) * (H * W), zb = (min(max(z0, -1) + 1, D - 1)) * (H * W);
+    s.off[0] = za + ya + xa; s.off[1] = za + ya + xb; s.off[2] = za + yb + xa; s.off[3] = za + yb + xb;
+    s.off[4] = zb + ya + xa; s.off[5] = zb + ya + xb; s.off[6] = zb + yb + xa; s.off[7] = zb + yb + xb;
+    s.w[0] = __fmul_rn(w00, wz0); s.w[1] = __fmul_rn(w10, wz0); s.w[2] = __fmul_rn(w01, wz0); s.w[3] = __fmul_rn(w11, wz0);
+    s.w[4] = __fmul_rn(w00, wz1); s.w[5] = __fmul_rn(w10, wz1); s.w[6] = __fmul_rn(w01, wz1); s.w[7] = __fmul_rn(w11, wz1);
+  } else {
+    s.off[0] = ya + xa; s.off[1] = ya + xb; s.off[2] = yb + xa; s.off[3] = yb + xb;
+    s.w[0] = w00; s.w[1] = w10; s.w[2] = w01; s.w[3] = w11;
+  }
+}
+template <bool IS3D, bool READONLY>
+__device__ __forceinline__ float sample8(const float* __restrict__ plane, const Stencil8& s) {
+  float acc = 0.0f;
+#pragma unroll
+  for (int k = 0; k < (IS3D ? 8 : 4); ++k) {
+    const float v = READONLY ? __ldg(plane + s.off[k]) : plane[s.off[k]];
+    acc = __fadd_rn(acc, __fmul_rn(v, s.w[k]));
+  }
+  return acc;
+}
+
 // nearest index (round half to even) or -1 when outside the volume
 template <bool IS3D>
 __device__ __forceinline__ ptrdiff_t nearest_index(float cx, float cy, float cz, const Vol& s) {

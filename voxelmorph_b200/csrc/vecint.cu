@@ -71,23 +71,13 @@ __global__ void __launch_bounds__(256) vecint_fwd_kernel(const float* __restrict
         const float* fb = cur + (size_t)b * g.nd * g.vol.DHW;
         float fv[3], cx, cy, cz;
         field_coords<IS3D, ARITH>(fb, p, x, y, z, g, fv, cx, cy, cz);
-        Stencil st = make_stencil<IS3D>(cx, cy, cz, g.vol);
+        Stencil8 st;
+        make_stencil8<IS3D>(cx, cy, cz, g.vol.D, g.vol.H, g.vol.W, st);
         float* ob = nxt + (size_t)b * g.nd * g.vol.DHW + p;
 #pragma unroll
         for (int c = 0; c < (IS3D ? 3 : 2); ++c) {
           // plain (coherent) loads: `cur` was written earlier in this same launch
-          constexpr int NC = IS3D ? 8 : 4;
-          const float* plane = fb + (size_t)c * g.vol.DHW;
-          float acc = 0.0f;
-          ptrdiff_t base = corner_offset(st, 0, g.vol);
-#pragma unroll
-          for (int k = 0; k < NC; ++k) {
-            if (st.mask & (1u << k)) {
-              ptrdiff_t off = base + ((k >> 2) & 1) * (ptrdiff_t)g.vol.HW + ((k >> 1) & 1) * (ptrdiff_t)g.vol.W + (k & 1);
-              acc = __fadd_rn(acc, __fmul_rn(plane[off], corner_weight<IS3D>(st, k)));
-            }
-          }
-          ob[(size_t)c * g.vol.DHW] = __fadd_rn(fv[c], acc);
+          ob[(size_t)c * g.vol.DHW] = __fadd_rn(fv[c], sample8<IS3D, false>(fb + (size_t)c * g.vol.DHW, st));
         }
       }
     }

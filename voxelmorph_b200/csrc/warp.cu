@@ -45,9 +45,10 @@ __global__ void __launch_bounds__(TX* TY) warp_fwd_kernel(const float* __restric
     ptrdiff_t idx = nearest_index<IS3D>(cx, cy, cz, g.src);
     for (int c = 0; c < g.C; ++c) ob[(size_t)c * g.dst.DHW] = idx >= 0 ? __ldg(sb + (size_t)c * g.src.DHW + idx) : 0.0f;
   } else {
-    Stencil st = make_stencil<IS3D>(cx, cy, cz, g.src);
+    Stencil8 st;
+    make_stencil8<IS3D>(cx, cy, cz, g.src.D, g.src.H, g.src.W, st);
     for (int c = 0; c < g.C; ++c)
-      ob[(size_t)c * g.dst.DHW] = sample_linear<IS3D>(sb + (size_t)c * g.src.DHW, st, g.src);
+      ob[(size_t)c * g.dst.DHW] = sample8<IS3D, true>(sb + (size_t)c * g.src.DHW, st);
   }
 }
 
@@ -124,6 +125,7 @@ static int check_geom(int B, int C, int Ds, int Hs, int Ws, int D, int H, int W,
   VXM_REQUIRE(B > 0 && C > 0 && Ds > 0 && Hs > 0 && Ws > 0 && D > 0 && H > 0 && W > 0, "warp: non-positive dimension");
   VXM_REQUIRE(nd == 3 || (D == 1 && Ds == 1), "warp: a 2-D problem must be passed with D == 1");
   VXM_REQUIRE((size_t)D * B <= 65535u, "warp: D*B exceeds the launch grid limit (65535)");
+  VXM_REQUIRE((size_t)Ds * Hs * Ws < (1u << 31) && (size_t)D * H * W < (1u << 31), "warp: volume exceeds 2^31 voxels");
   return VXM_OK;
 }
 

@@ -224,12 +224,12 @@ def backward_tape(ctx, g_flow):
                 graw[t] = tc.conv_fwd(g_in, None, wpk, NP, None, cv.cin, kd, planar=g_in_planar)
         else:
             ca = cv.xa.shape[-1]
-            wa, NPa = _cache.get(cv.w, "dgrad_a", lambda: tc.pack_weights(w[:, :ca].contiguous(), transposed=True))
-            wb, NPb = _cache.get(cv.w, "dgrad_b", lambda: tc.pack_weights(w[:, ca:].contiguous(), transposed=True))
-            g_up = tc.conv_fwd(g_in, None, wa, NPa, None, ca, kd, planar=g_in_planar)             # grad wrt upsample(a), fine res
-            gz[cv.a_id] = _sumpool_mask(g_up, tensors[cv.a_id], nd, _slope_of(ctx, cv.a_id))
+            # single dgrad pass over the whole concat input: N = Ca + Cb output channels, split on store
+            wpk, NP = _cache.get(cv.w, "dgrad", lambda: tc.pack_weights(w, transposed=True))
+            g_up, g_sk = tc.conv_fwd(g_in, None, wpk, NP, None, cv.cin, kd, planar=g_in_planar, split=ca)
+            gz[cv.a_id] = _sumpool_mask(g_up, tensors[cv.a_id], nd, _slope_of(ctx, cv.a_id))   # grad wrt upsample(a): sum children
             del g_up
-            gskip[cv.b_id] = tc.conv_fwd(g_in, None, wb, NPb, None, cv.cin - ca, kd, planar=g_in_planar)
+            gskip[cv.b_id] = g_sk
     return grads
 
 

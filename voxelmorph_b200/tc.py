@@ -17,7 +17,11 @@ def np_for(cout):
         return 16
     if cout <= 32:
         return 32
-    raise _lib.VxmError("tcgen05 conv engine: at most 32 output channels per layer (got %d)" % cout)
+    if cout <= 48:
+        return 48
+    if cout <= 64:
+        return 64
+    raise _lib.VxmError("tcgen05 conv engine: at most 64 output channels per launch (got %d)" % cout)
 
 
 def to_ndhwc_bf16(x):
@@ -45,7 +49,7 @@ def pack_weights(w, transposed=False):
     return out, NP
 
 
-def conv_fwd(xa, xb, wpk, NP, bias, cout, kd, up=False, planar=None, out_fp32_planar=False, slope=None, mask=None):
+def conv_fwd(xa, xb, wpk, NP, bias, cout, kd, up=False, planar=None, out_fp32_planar=False, slope=None, mask=None, split=None):
     """Launch the tensor-core convolution.  xa / xb: bf16 NDHWC tensors (xa at half resolution when `up`);
     planar: list of <= 4 fp32 (B,1,D,H,W) tensors used instead of xa/xb.  Returns bf16 NDHWC (B,D,H,W,cout)
     or, with out_fp32_planar, fp32 (B,cout,D,H,W)."""
@@ -66,15 +70,20 @@ def conv_fwd(xa, xb, wpk, NP, bias, cout, kd, up=False, planar=None, out_fp32_pl
         Cb = 0 if xb is None else xb.shape[-1]
         xf, xs, npl = None, None, 0
         dev = full.device
+    out2 = None
     if out_fp32_planar:
         out = torch.empty((B, cout, D, H, W), dtype=torch.float32, device=dev)
+    elif split:
+        out = torch.empty((B, D, H, W, split), dtype=torch.bfloat16, device=dev)
+        out2 = torch.empty((B, D, H, W, cout - split), dtype=torch.bfloat16, device=dev)
     else:
         out = torch.empty((B, D, H, W, cout), dtype=torch.bfloat16, device=dev)
     s = -1.0 if slope is None else float(slope)
     _lib.check(lib.vxm_conv3d_tc_fwd(_lib.ptr(xa), _lib.ptr(xb), xf, xs, npl, _lib.ptr(wpk), _lib.ptr(bias), _lib.ptr(out),
                                      _lib.ptr(mask), B, D, H, W, Ca, Cb, 1 if up else 0, cout, NP, kd,
-                                     1 if out_fp32_planar else 0, s, _lib.stream_ptr()), "vxm_conv3d_tc_fwd")
-    return out
+                                     1 if out_fp32_planar else 0, s, _lib.ptr(out2), int(split or 0), _lib.stream_ptr()),
+               "vxm_conv3d_tc_fwd")
+    return (out, out2) if split else out
 
 
 def _planar_args(planar):
