@@ -333,13 +333,13 @@ def b200_arm(args):
             return fn(*a, **k)
         return inner
 
-    o_cf, o_cw = tcmod.conv_fwd, tcmod.conv_wgrad
+    o_cf, o_cw, o_ct = tcmod.conv_fwd, tcmod.conv_wgrad, tcmod.conv_fwd_t
     orig_fwd, orig_bwd = ops._ConvK3Fn.forward, ops._ConvK3Fn.backward
     conv_total_ms = None
     if ops.conv_engine() == "bf16":
-        tcmod.conv_fwd, tcmod.conv_wgrad = recording(o_cf), recording(o_cw)
+        tcmod.conv_fwd, tcmod.conv_wgrad, tcmod.conv_fwd_t = recording(o_cf), recording(o_cw), recording(o_ct)
         eager_step(*pairs_dev[0])
-        tcmod.conv_fwd, tcmod.conv_wgrad = o_cf, o_cw
+        tcmod.conv_fwd, tcmod.conv_wgrad, tcmod.conv_fwd_t = o_cf, o_cw, o_ct
         torch.cuda.synchronize()
         reps = []
         for _ in range(3):
@@ -353,6 +353,13 @@ def b200_arm(args):
             reps.append(c0.elapsed_time(c1))
         conv_total_ms = statistics.median(reps)
         n_conv_launches = len(calls)
+        if os.environ.get("VXM_BENCH_VERBOSE") and rank == 0:
+            for fn, a, k in calls:      # per-launch breakdown (stderr)
+                torch.cuda._sleep(2000000)
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record(); fn(*a, **k); c1.record(); torch.cuda.synchronize()
+                shp = [tuple(x.shape) for x in a[:3] if hasattr(x, "shape")]
+                print("  %-12s %8.1f us  %s" % (fn.__name__, c0.elapsed_time(c1) * 1e3, shp), file=sys.stderr)
         del calls
     else:
         conv_ms = []

@@ -156,6 +156,16 @@ int vxm_conv3d_tc_fwd(const void* xa, const void* xb, const float* const* xf, co
                       int out_mode, float slope, void* out2, int csplit, void* stream);
 /* out2 != NULL (bf16 outputs only): channels [0,csplit) go to `out` (B,D,H,W,csplit) and [csplit,Cout) to `out2`
  * (B,D,H,W,Cout-csplit) — the single-pass dgrad of a layer whose input was a channel concat; np may then be 48 or 64. */
+/* "kw-stacked" variant of the tensor-core convolution (Cin in {8,16,32,48,64}, Cout <= 64): the three kw taps are
+ * stacked along the MMA N dimension (N = 3*coutp), the K loop runs over (kd,kh,Cin/16) only and the kw shift is a warp
+ * shuffle in the epilogue — the activation operand is read 9x instead of 27x.  Same inputs / outputs / epilogue options
+ * as vxm_conv3d_tc_fwd (no planar sources); weights are packed by vxm_conv3d_tct_pack (coutp in {16,32,48,64}). */
+size_t vxm_conv3d_tct_packed_bytes(int cin_eff, int coutp, int kd);
+int vxm_conv3d_tct_pack(const float* w, void* wpk, int Cout, int Cin, int kd, int coutp, int transposed, void* stream);
+int vxm_conv3d_tct_supported(int Ca, int Cb, int Cout);
+int vxm_conv3d_tct_fwd(const void* xa, const void* xb, const void* wpk, const float* bias, void* out, const void* mask,
+                       int B, int D, int H, int W, int Ca, int Cb, int up, int Cout, int coutp, int kd, int out_mode,
+                       float slope, void* out2, int csplit, void* stream);
 /* Weight (and bias) gradient on tensor cores.  x sources as in vxm_conv3d_tc_fwd (the layer's forward input);
  * gz = gradient w.r.t. the convolution output (already multiplied by the activation derivative): bf16 NDHWC with
  * Cg in {8,16,32} channels, or nplanar_g (<= 4) planar fp32 volumes (flow head).  grad_w: fp32

@@ -80,6 +80,12 @@ class _Conv:
 
 def _run_conv(cv, kd):
     """Forward of one tape entry."""
+    ca = 0 if cv.xa is None else cv.xa.shape[-1]
+    cb = 0 if cv.xb is None else cv.xb.shape[-1]
+    if cv.planar is None and tc.use_t_kernel(ca, cb, cv.cout):
+        wpk, cp = _cache.get(cv.w, "fwd_t", lambda: tc.pack_weights_t(cv.w.detach()))
+        return tc.conv_fwd_t(cv.xa, cv.xb, wpk, cp, cv.b.detach() if cv.b is not None else None, cv.cout, kd, up=cv.up,
+                             out_fp32_planar=cv.planar_out, slope=cv.slope)
     wpk, NP = _cache.get(cv.w, "fwd", lambda: tc.pack_weights(cv.w.detach()))
     return tc.conv_fwd(cv.xa, cv.xb, wpk, NP, cv.b.detach() if cv.b is not None else None, cv.cout, kd, up=cv.up, planar=cv.planar,
                        out_fp32_planar=cv.planar_out, slope=cv.slope)
@@ -217,16 +223,27 @@ def backward_tape(ctx, g_flow):
         w = cv.w.detach()
         if cv.b_id is None:
             t = cv.a_id
-            wpk, NP = _cache.get(cv.w, "dgrad", lambda: tc.pack_weights(w, transposed=True))
-            if producer[t] == "conv":
-                gz[t] = tc.conv_fwd(g_in, None, wpk, NP, None, cv.cin, kd, planar=g_in_planar, slope=_slope_of(ctx, t), mask=tensors[t])
+            msk = tensors[t] if producer[t] == "conv" else None
+            sl = _slope_of(ctx, t) if producer[t] == "conv" else None
+            if tc.use_t_kernel(g_in.shape[-1], 0, cv.cin):
+                wpk, cp = _cache.get(cv.w, "dgrad_t", lambda: tc.pack_weights_t(w, transposed=True))
+                res = tc.conv_fwd_t(g_in, None, wpk, cp, None, cv.cin, kd, slope=sl, mask=msk)
             else:
-                graw[t] = tc.conv_fwd(g_in, None, wpk, NP, None, cv.cin, kd, planar=g_in_planar)
+                wpk, NP = _cache.get(cv.w, "dgrad", lambda: tc.pack_weights(w, transposed=True))
+                res = tc.conv_fwd(g_in, None, wpk, NP, None, cv.cin, kd, planar=g_in_planar, slope=sl, mask=msk)
+            if producer[t] == "conv":
+                gz[t] = res
+            else:
+                graw[t] = res
         else:
             ca = cv.xa.shape[-1]
             # single dgrad pass over the whole concat input: N = Ca + Cb output channels, split on store
-            wpk, NP = _cache.get(cv.w, "dgrad", lambda: tc.pack_weights(w, transposed=True))
-            g_up, g_sk = tc.conv_fwd(g_in, None, wpk, NP, None, cv.cin, kd, planar=g_in_planar, split=ca)
+            if tc.use_t_kernel(g_in.shape[-1], 0, cv.cin):
+                wpk, cp = _cache.get(cv.w, "dgrad_t", lambda: tc.pack_weights_t(w, transposed=True))
+                g_up, g_sk = tc.conv_fwd_t(g_in, None, wpk, cp, None, cv.cin, kd, split=ca)
+            else:
+                wpk, NP = _cache.get(cv.w, "dgrad", lambda: tc.pack_weights(w, transposed=True))
+                g_up, g_sk = tc.conv_fwd(g_in, None, wpk, NP, None, cv.cin, kd, planar=g_in_planar, split=ca)
             gz[cv.a_id] = _sumpool_mask(g_up, tensors[cv.a_id], nd, _slope_of(ctx, cv.a_id))   # grad wrt upsample(a): sum children
             del g_up
             gskip[cv.b_id] = g_sk

@@ -136,3 +136,53 @@ def planar_to_ndhwc8(planes):
     _lib.check(lib.vxm_planar_to_ndhwc8_bf16(arr_p, arr_s, n, _lib.ptr(out), B, D * H * W, _lib.stream_ptr()),
                "vxm_planar_to_ndhwc8_bf16")
     return out
+
+
+# ---- weights-stationary ("transposed") kernel: Cin in {8,16,32,48}, Cout <= 32 -------------------------------------
+
+def use_t_kernel(ca, cb, cout):
+    """Kernel choice for one convolution launch: VXM_B200_TC_KERNEL = auto (default) | t | n."""
+    import os
+    mode = os.environ.get("VXM_B200_TC_KERNEL", "auto")
+    if mode == "n":
+        return False
+    return bool(_lib.load().vxm_conv3d_tct_supported(ca, cb, cout))
+
+
+def pack_weights_t(w, transposed=False):
+    lib = _lib.load()
+    if w.dim() == 4:
+        w = w.unsqueeze(2)
+    w = w.contiguous()
+    Cout, Cin, kd = w.shape[0], w.shape[1], w.shape[2]
+    cin_eff, nout = (Cout, Cin) if transposed else (Cin, Cout)
+    coutp = 16 if nout <= 16 else (32 if nout <= 32 else (48 if nout <= 48 else 64))
+    nbytes = int(lib.vxm_conv3d_tct_packed_bytes(cin_eff, coutp, kd))
+    out = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
+    _lib.check(lib.vxm_conv3d_tct_pack(_lib.ptr(w), _lib.ptr(out), Cout, Cin, kd, coutp, 1 if transposed else 0,
+                                       _lib.stream_ptr()), "vxm_conv3d_tct_pack")
+    return out, coutp
+
+
+def conv_fwd_t(xa, xb, wpk, coutp, bias, cout, kd, up=False, out_fp32_planar=False, slope=None, mask=None, split=None):
+    lib = _lib.load()
+    full = xb if xb is not None else xa
+    B, D, H, W = full.shape[0], full.shape[1], full.shape[2], full.shape[3]
+    if xb is None and up:
+        D, H, W = (D * 2 if kd == 3 else D), H * 2, W * 2
+    Ca = 0 if xa is None else xa.shape[-1]
+    Cb = 0 if xb is None else xb.shape[-1]
+    dev = full.device
+    out2 = None
+    if out_fp32_planar:
+        out = torch.empty((B, cout, D, H, W), dtype=torch.float32, device=dev)
+    elif split:
+        out = torch.empty((B, D, H, W, split), dtype=torch.bfloat16, device=dev)
+        out2 = torch.empty((B, D, H, W, cout - split), dtype=torch.bfloat16, device=dev)
+    else:
+        out = torch.empty((B, D, H, W, cout), dtype=torch.bfloat16, device=dev)
+    s = -1.0 if slope is None else float(slope)
+    _lib.check(lib.vxm_conv3d_tct_fwd(_lib.ptr(xa), _lib.ptr(xb), _lib.ptr(wpk), _lib.ptr(bias), _lib.ptr(out), _lib.ptr(mask),
+                                      B, D, H, W, Ca, Cb, 1 if up else 0, cout, coutp, kd, 1 if out_fp32_planar else 0, s,
+                                      _lib.ptr(out2), int(split or 0), _lib.stream_ptr()), "vxm_conv3d_tct_fwd")
+    return (out, out2) if split else out
