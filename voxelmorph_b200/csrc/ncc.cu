@@ -40,8 +40,8 @@ template <int MODE, int WD>
 __global__ void __launch_bounds__(256) ncc_kernel(NccArgs a) {
   constexpr int NF = MODE == 0 ? 2 : 3;
   constexpr int NS = MODE == 0 ? 5 : 3;
-  __shared__ float s_in[NF][NIH][NIW];
-  __shared__ float s_w[NS][NIH][NTW];
+  __shared__ __align__(16) float s_in[NF][NIH][NIW];
+  __shared__ __align__(16) float s_w[NS][NIH + 2][NTW];
   __shared__ double s_red[32];
 
   const int tid = threadIdx.x;
@@ -85,34 +85,58 @@ __global__ void __launch_bounds__(256) ncc_kernel(NccArgs a) {
             if (NF == 3) s_in[2][r][c] = ok ? __ldg(f2 + off) : 0.f;
           }
           __syncthreads();
-          // ---- W pass ----
-          for (int idx = tid; idx < rows_in * NTW; idx += 256) {
-            int r = idx >> 5, c = idx & 31;
-            float acc[NS];
+          // ---- W pass: each thread forms 4 adjacent window sums of one row from 12 staged values (register blocked) ----
+          if (tid < rows_in * (NTW / 4)) {
+            const int r = tid >> 3, c4 = (tid & 7) * 4;
+            float x0[12], x1[12], x2[12];
 #pragma unroll
-            for (int s = 0; s < NS; ++s) acc[s] = 0.f;
-            for (int k = 0; k < a.ww; ++k) {
-              float x0 = s_in[0][r][c + k], x1 = s_in[1][r][c + k];
-              if (MODE == 0) {
-                acc[0] += x0; acc[1] += x1; acc[2] += x0 * x0; acc[3] += x1 * x1; acc[4] += x0 * x1;
-              } else {
-                acc[0] += x0; acc[1] += x1; acc[2] += s_in[NF - 1][r][c + k];
+            for (int q = 0; q < 3; ++q) {
+              const float4 a4 = *reinterpret_cast<const float4*>(&s_in[0][r][c4 + 4 * q]);
+              const float4 b4 = *reinterpret_cast<const float4*>(&s_in[1][r][c4 + 4 * q]);
+              x0[4 * q] = a4.x; x0[4 * q + 1] = a4.y; x0[4 * q + 2] = a4.z; x0[4 * q + 3] = a4.w;
+              x1[4 * q] = b4.x; x1[4 * q + 1] = b4.y; x1[4 * q + 2] = b4.z; x1[4 * q + 3] = b4.w;
+              if (MODE == 1) {
+                const float4 c4v = *reinterpret_cast<const float4*>(&s_in[NF - 1][r][c4 + 4 * q]);
+                x2[4 * q] = c4v.x; x2[4 * q + 1] = c4v.y; x2[4 * q + 2] = c4v.z; x2[4 * q + 3] = c4v.w;
+              }
+            }
+            float acc[NS][4];
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+#pragma unroll
+              for (int o = 0; o < 4; ++o) acc[s][o] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+              if (k < a.ww) {
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                  const float u = x0[o + k], v = x1[o + k];
+                  if (MODE == 0) {
+                    acc[0][o] += u; acc[1][o] += v; acc[2][o] += u * u; acc[3][o] += v * v; acc[4][o] += u * v;
+                  } else {
+                    acc[0][o] += u; acc[1][o] += v; acc[2][o] += x2[o + k];
+                  }
+                }
               }
             }
 #pragma unroll
-            for (int s = 0; s < NS; ++s) s_w[s][r][c] = acc[s];
+            for (int s = 0; s < NS; ++s)
+              *reinterpret_cast<float4*>(&s_w[s][r][c4]) = make_float4(acc[s][0], acc[s][1], acc[s][2], acc[s][3]);
           }
           __syncthreads();
-          // ---- H pass -> ring slot j ----
+          // ---- H pass -> ring slot j: two ADJACENT rows per thread share their 10 loads ----
 #pragma unroll
-          for (int o = 0; o < 2; ++o) {
-            int r = ty + 8 * o;
+          for (int s = 0; s < NS; ++s) {
+            float col[10];
 #pragma unroll
-            for (int s = 0; s < NS; ++s) {
-              float acc = 0.f;
-              for (int k = 0; k < a.wh; ++k) acc += s_w[s][r + k][tx];
-              ring[o][j][s] = acc;
+            for (int k = 0; k < 10; ++k) col[k] = s_w[s][2 * ty + k][tx];
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+              if (k < a.wh) { a0 += col[k]; a1 += col[k + 1]; }
             }
+            ring[0][j][s] = a0;
+            ring[1][j][s] = a1;
           }
         } else {
 #pragma unroll
@@ -125,7 +149,7 @@ __global__ void __launch_bounds__(256) ncc_kernel(NccArgs a) {
         if (zo >= z0) {
 #pragma unroll
           for (int o = 0; o < 2; ++o) {
-            int h = h0 + ty + 8 * o, w = w0 + tx;
+            int h = h0 + 2 * ty + o, w = w0 + tx;
             if (h < a.H && w < a.W) {
               float S[NS];
 #pragma unroll
