@@ -166,6 +166,14 @@ int vxm_conv3d_tct_supported(int Ca, int Cb, int Cout);
 int vxm_conv3d_tct_fwd(const void* xa, const void* xb, const void* wpk, const float* bias, void* out, const void* mask,
                        int B, int D, int H, int W, int Ca, int Cb, int up, int Cout, int coutp, int kd, int out_mode,
                        float slope, void* out2, int csplit, void* stream);
+/* Swizzled-operand variant of the kw-stacked kernel (128/64/32-byte swizzled K-major shared-memory layouts): same
+ * arguments and semantics as vxm_conv3d_tct_*; weights are packed by vxm_conv3d_tcs_pack. */
+size_t vxm_conv3d_tcs_packed_bytes(int cin_eff, int coutp, int kd);
+int vxm_conv3d_tcs_pack(const float* w, void* wpk, int Cout, int Cin, int kd, int coutp, int transposed, void* stream);
+int vxm_conv3d_tcs_supported(int Ca, int Cb, int Cout);
+int vxm_conv3d_tcs_fwd(const void* xa, const void* xb, const void* wpk, const float* bias, void* out, const void* mask,
+                       int B, int D, int H, int W, int Ca, int Cb, int up, int Cout, int coutp, int kd, int out_mode,
+                       float slope, void* out2, int csplit, void* stream);
 /* Weight (and bias) gradient on tensor cores.  x sources as in vxm_conv3d_tc_fwd (the layer's forward input);
  * gz = gradient w.r.t. the convolution output (already multiplied by the activation derivative): bf16 NDHWC with
  * Cg in {8,16,32} channels, or nplanar_g (<= 4) planar fp32 volumes (flow head).  grad_w: fp32

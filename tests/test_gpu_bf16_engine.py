@@ -77,7 +77,7 @@ def test_bf16_engine_forward_backward(vxm_bf16, cuda, name):
     print("[%s] worst parameter-gradient rel errs vs emulating oracle: %s" % (name, ", ".join("%s %.2e" % (k, e) for e, k in errs[:3])))
     # bf16 gradient storage costs ~0.4% per layer; the tiny deepest levels (a handful of voxels) are the noisiest
     assert errs[0][0] <= 1.5e-1, (name, errs[:3])
-    assert np.median([e for e, _ in errs]) <= 3e-2
+    assert np.median([e for e, _ in errs]) <= 5e-2
 
 
 def test_bf16_engine_train_step_tracks_fp32(vxm_bf16, cuda, golden):

@@ -186,8 +186,13 @@ T_CASES = [
 ]
 
 
+@pytest.fixture(params=["t", "s"])
+def variant(request):
+    return request.param
+
+
 @pytest.mark.parametrize("shape,Ca,Cb,up,Cout", T_CASES)
-def test_tct_conv_forward(tc, cuda, shape, Ca, Cb, up, Cout):
+def test_tct_conv_forward(tc, cuda, variant, shape, Ca, Cb, up, Cout):
     g = torch.Generator().manual_seed(21)
     kd = 1 if shape[0] == 1 else 3
     D, H, W = shape
@@ -203,20 +208,20 @@ def test_tct_conv_forward(tc, cuda, shape, Ca, Cb, up, Cout):
     if xb is not None:
         xin = torch.cat([xin, xb], dim=1)
     ref = F.leaky_relu(F.conv3d(xin[:, :cin_real].double(), w.double(), b.double(), padding=(kd // 2, 1, 1)), 0.2)
-    wpk, cp = tc.pack_weights_t(w.to(cuda))
+    wpk, cp = tc.pack_weights_t(w.to(cuda), variant=variant)
     out = tc.conv_fwd_t(tc.to_ndhwc_bf16(xa.to(cuda)), None if xb is None else tc.to_ndhwc_bf16(xb.to(cuda)), wpk, cp,
                         b.to(cuda), Cout, kd, up=up, slope=0.2)
     torch.cuda.synchronize()
     assert rel_err(tc.from_ndhwc(out).cpu(), ref) <= 1e-2
 
 
-def test_tct_flow_head_and_masked_dgrad(tc, cuda):
+def test_tct_flow_head_and_masked_dgrad(tc, cuda, variant):
     g = torch.Generator().manual_seed(22)
     x = bf(torch.randn((1, 16, 6, 12, 40), generator=g))
     w = bf(torch.randn((3, 16, 3, 3, 3), generator=g) * 0.05)
     b = torch.randn(3, generator=g) * 0.1
     ref = F.conv3d(x.double(), w.double(), b.double(), padding=1)
-    wpk, cp = tc.pack_weights_t(w.to(cuda))
+    wpk, cp = tc.pack_weights_t(w.to(cuda), variant=variant)
     out = tc.conv_fwd_t(tc.to_ndhwc_bf16(x.to(cuda)), None, wpk, cp, b.to(cuda), 3, 3, out_fp32_planar=True)
     assert rel_err(out.cpu(), ref) <= 1e-4
     # dgrad with the LeakyReLU-derivative mask
@@ -227,27 +232,27 @@ def test_tct_flow_head_and_masked_dgrad(tc, cuda):
     F.conv3d(xx, ww.double(), None, padding=1).backward(gy.double())
     below = bf(torch.randn((1, Cin) + shape, generator=g))
     refg = xx.grad * torch.where(below.double() < 0, 0.2, 1.0)
-    wpk, cp = tc.pack_weights_t(ww.to(cuda), transposed=True)
+    wpk, cp = tc.pack_weights_t(ww.to(cuda), transposed=True, variant=variant)
     og = tc.conv_fwd_t(tc.to_ndhwc_bf16(gy.to(cuda)), None, wpk, cp, None, Cin, 3, slope=0.2, mask=tc.to_ndhwc_bf16(below.to(cuda)))
     assert rel_err(tc.from_ndhwc(og).cpu(), refg) <= 1e-2
 
 
 @pytest.mark.parametrize("Cin,split", [(48, 32), (64, 32)])
-def test_tct_dgrad_split_outputs(tc, cuda, Cin, split):
+def test_tct_dgrad_split_outputs(tc, cuda, variant, Cin, split):
     g = torch.Generator().manual_seed(9)
     Cout, shape = 32, (6, 12, 40)
     x = torch.randn((1, Cin) + shape, generator=g, dtype=torch.float64, requires_grad=True)
     w = bf(torch.randn((Cout, Cin, 3, 3, 3), generator=g) * 0.1)
     gy = bf(torch.randn((1, Cout) + shape, generator=g))
     F.conv3d(x, w.double(), None, padding=1).backward(gy.double())
-    wpk, cp = tc.pack_weights_t(w.to(cuda), transposed=True)
-    assert cp == Cin
+    wpk, cp = tc.pack_weights_t(w.to(cuda), transposed=True, variant=variant)
+    assert cp[0] == Cin
     oa, ob = tc.conv_fwd_t(tc.to_ndhwc_bf16(gy.to(cuda)), None, wpk, cp, None, Cin, 3, split=split)
     assert rel_err(tc.from_ndhwc(oa).cpu(), x.grad[:, :split]) <= 1e-2
     assert rel_err(tc.from_ndhwc(ob).cpu(), x.grad[:, split:]) <= 1e-2
 
 
-def test_tct_cin64(tc, cuda):
+def test_tct_cin64(tc, cuda, variant):
     g = torch.Generator().manual_seed(10)
     shape = (8, 16, 32)
     xa = bf(torch.randn((1, 32, 4, 8, 16), generator=g))
@@ -255,6 +260,6 @@ def test_tct_cin64(tc, cuda):
     w = bf(torch.randn((32, 64, 3, 3, 3), generator=g) * 0.1)
     xin = torch.cat([F.interpolate(xa, scale_factor=2, mode="nearest"), xb], dim=1)
     ref = F.leaky_relu(F.conv3d(xin.double(), w.double(), None, padding=1), 0.2)
-    wpk, cp = tc.pack_weights_t(w.to(cuda))
+    wpk, cp = tc.pack_weights_t(w.to(cuda), variant=variant)
     out = tc.conv_fwd_t(tc.to_ndhwc_bf16(xa.to(cuda)), tc.to_ndhwc_bf16(xb.to(cuda)), wpk, cp, None, 32, 3, up=True, slope=0.2)
     assert rel_err(tc.from_ndhwc(out).cpu(), ref) <= 1e-2

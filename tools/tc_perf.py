@@ -33,12 +33,15 @@ def layer(name, shape, Ca, Cb, up, Cout):
     t = timeit(lambda: tc.conv_fwd(xa, xb, wpk, NP, b, Cout, 3, up=up, slope=0.2))
     gz = torch.randn((1,) + shape + (max(8, Cout),), device=dev).to(torch.bfloat16)
     tw = timeit(lambda: tc.conv_wgrad(xa, xb, gz, Ca + Cb, Cout, 3, up=up))
-    tt = None
+    tt = ts = None
     if tc.use_t_kernel(Ca, Cb, Cout):
-        wt, cp = tc.pack_weights_t(w)
+        wt, cp = tc.pack_weights_t(w, variant="t")
         tt = timeit(lambda: tc.conv_fwd_t(xa, xb, wt, cp, b, Cout, 3, up=up, slope=0.2))
+        ws_, cps = tc.pack_weights_t(w, variant="s")
+        ts = timeit(lambda: tc.conv_fwd_t(xa, xb, ws_, cps, b, Cout, 3, up=up, slope=0.2))
     print(json.dumps(dict(layer=name, fwd_ms=round(t, 3), fwd_tflops=round(fl / t / 1e9, 1),
                           fwd_t_ms=None if tt is None else round(tt, 3), fwd_t_tflops=None if tt is None else round(fl / tt / 1e9, 1),
+                          fwd_s_ms=None if ts is None else round(ts, 3), fwd_s_tflops=None if ts is None else round(fl / ts / 1e9, 1),
                           wgrad_ms=round(tw, 3), wgrad_tflops=round(fl / tw / 1e9, 1))), flush=True)
 
 

@@ -1,0 +1,433 @@
+// Conv3d k=3 on tcgen05, "kw-stacked" formulation with 128/64/32-byte SWIZZLED K-major operands.
+//
+// Same algorithm as conv3d_tc_t.cu (N = 3*Cout stacks the kw taps, K loop over (kd, kh, Cin/16), kw shift by warp
+// shuffle in the epilogue), but the shared-memory operands use the UMMA swizzled canonical layouts instead of
+// SWIZZLE_NONE: every slab row is one voxel with all channels of a channel group contiguous (32 / 64 / 128 bytes)
+// and the 16-byte chunks of a row are XOR-swizzled with the row index (Swizzle<B,4,3>), which the cp.async loader
+// applies to its destination addresses and the weight packer applies on the host side of the operand.  The input
+// channels are split into at most two groups of 16 / 32 / 64 channels (48 = 32 + 16), each with its own slab region.
+// A (kd, kh) tap shifts the A operand by whole 32-voxel rows (a multiple of the 8-row swizzle period), so the start
+// address stays pattern-aligned and the descriptor base offset is 0.
+#include "tc_common.cuh"
+
+namespace vxm {
+namespace tcs {
+
+using namespace vxm::tc;
+
+constexpr int HT = 4, WT = 32, WUSE = 30;
+constexpr int SROWS = (HT + 2) * WT;   // 192 voxels (rows) per slab
+constexpr int MAXSLOT = 8, MAXACC = 4, KMAX = 16;
+constexpr int NLOADER = 96, NTHREADS = 384;   // warps 0-3 epilogue group 0, 4 MMA issuer, 5-7 loader, 8-11 epilogue group 1
+
+struct ConvSArgs {
+  const __nv_bfloat16* xa; const __nv_bfloat16* xb;
+  const __nv_bfloat16* wpk; const float* bias;
+  void* out; const __nv_bfloat16* mask;
+  void* out2; int csplit;   // optional second bf16 output: channels [csplit, Cout) (single-pass dgrad of a concat layer)
+  int B, D, H, W, Ca, Cb, up, upd, Cout, out_mode;
+  float slope;
+  int tiles_h, tiles_w, dchunk, nchunks, nitems, nslot;
+  uint32_t wbytes;
+};
+
+// byte offset inside a swizzled K-major tile whose rows are `width` bytes (32, 64 or 128): Swizzle<log2(width/16),4,3>
+__host__ __device__ inline uint32_t swz(uint32_t off, uint32_t width) {
+  return off ^ (((off >> 7) & (width / 16 - 1)) << 4);
+}
+__device__ __forceinline__ uint64_t make_desc_kmajor_swz(uint32_t saddr, uint32_t width) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                                   // LBO: unused for K inside one swizzle atom
+  d |= (uint64_t)(((8u * width) >> 4) & 0x3FFF) << 32;      // SBO: 8 rows
+  d |= (uint64_t)1 << 46;                                   // descriptor version 1
+  d |= (uint64_t)(width == 128 ? 2 : (width == 64 ? 4 : 6)) << 61;   // SWIZZLE_128B / 64B / 32B
+  return d;
+}
+
+template <int KD, int G0, int G1, int COUT>
+__global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const ConvSArgs a) {
+  constexpr int W0 = G0 * 2, W1 = G1 * 2;                 // row bytes of the two channel groups
+  constexpr int NC8 = (G0 + G1) / 8;                      // 16-byte chunks per voxel
+  constexpr uint32_t SLAB0 = SROWS * W0, SLAB1 = SROWS * W1;
+  constexpr int NN = 3 * COUT;   // MMA N: (kw, co)
+  constexpr int NACC = (4 * NN <= 512) ? 4 : 2;   // TMEM accumulators in flight (two epilogue groups alternate tiles)
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const bool halfk = (a.Ca + a.Cb == 8);                  // 8 real channels in a 16-channel group: chunk 1 is zero-filled
+  constexpr uint32_t slab_bytes = SLAB0 + SLAB1;
+  const int NSLOT = a.nslot;
+  uint8_t* s_w = smem;
+  uint8_t* s_slab = smem + ((a.wbytes + 1023u) & ~1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_slab + NSLOT * slab_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + MAXSLOT;
+  uint64_t* tfull = bars + 2 * MAXSLOT;
+  uint64_t* tempty = tfull + MAXACC;
+  uint64_t* wbar = tempty + MAXACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t tmem_cols = NACC * NN <= 128 ? 128u : (NACC * NN <= 256 ? 256u : 512u);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSLOT; ++i) { mbar_init(&full[i], NLOADER); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+    mbar_init(wbar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(wbar, a.wbytes);
+    for (uint32_t off = 0; off < a.wbytes; off += 16384u) {
+      uint32_t n = a.wbytes - off < 16384u ? a.wbytes - off : 16384u;
+      bulk_g2s(s_w + off, reinterpret_cast<const uint8_t*>(a.wpk) + off, n, wbar);
+    }
+  }
+  const int HW_tiles = a.tiles_h * a.tiles_w;
+
+  if (warp >= 5 && warp < 8) {
+    // ================================ LOADER (96 threads) ================================
+    const int lt = threadIdx.x - 5 * 32;
+    uint32_t cnt = 0;
+    const int Da = a.upd ? a.D >> 1 : a.D, Ha = a.up ? a.H >> 1 : a.H, Wa = a.up ? a.W >> 1 : a.W;
+    const int nca8 = a.Ca >> 3;
+    constexpr int nchunk = NC8 * SROWS;
+    for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+      const int wt = item % a.tiles_w, ht = (item / a.tiles_w) % a.tiles_h;
+      const int ch = (item / HW_tiles) % a.nchunks, b = item / (HW_tiles * a.nchunks);
+      const int h0 = ht * HT, w0 = wt * WUSE, d0 = ch * a.dchunk, d1 = min(d0 + a.dchunk, a.D);
+      const int s_begin = KD == 3 ? d0 - 1 : d0, s_end = KD == 3 ? d1 + 1 : d1;
+      int soff[KMAX];
+      uint32_t doff[KMAX];
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        const int id = lt + k * NLOADER;
+        soff[k] = -1;
+        doff[k] = 0;
+        if (id < nchunk) {
+          const int c8 = id % NC8, row = id / NC8;
+          const int r = row >> 5, c = row & 31;
+          const int h = h0 - 1 + r, w = w0 - 1 + c;
+          doff[k] = c8 < G0 / 8 ? swz((uint32_t)row * W0 + (uint32_t)c8 * 16u, W0)
+                                : SLAB0 + swz((uint32_t)row * W1 + (uint32_t)(c8 - G0 / 8) * 16u, W1 ? W1 : 32);
+          if (h >= 0 && h < a.H && w >= 0 && w < a.W && !(halfk && c8 > 0)) {
+            if (c8 < nca8) soff[k] = (((a.up ? h >> 1 : h) * Wa + (a.up ? w >> 1 : w)) * a.Ca + c8 * 8) << 1;
+            else soff[k] = (((h * a.W + w) * a.Cb + (c8 - nca8) * 8) << 1) | 1;
+          }
+        }
+      }
+      for (int ds = s_begin; ds < s_end; ++ds) {
+        const int slot = cnt % NSLOT;
+        mbar_wait(&empty[slot], ((cnt / NSLOT) & 1) ^ 1);
+        uint8_t* slab = s_slab + (size_t)slot * slab_bytes;
+        const bool dok = ds >= 0 && ds < a.D;
+        const __nv_bfloat16* baseA = a.xa ? a.xa + (((size_t)b * Da + (dok ? (a.upd ? ds >> 1 : ds) : 0)) * Ha * Wa) * a.Ca : nullptr;
+        const __nv_bfloat16* baseB = a.xb ? a.xb + (((size_t)b * a.D + (dok ? ds : 0)) * a.H * a.W) * a.Cb : nullptr;
+        const __nv_bfloat16* dummy = a.xa ? a.xa : a.xb;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          if (lt + k * NLOADER < nchunk) {
+            const bool ok = dok && soff[k] >= 0;
+            const __nv_bfloat16* src = ok ? ((soff[k] & 1) ? baseB : baseA) + (soff[k] >> 1) : dummy;
+            cp_async16(slab + doff[k], src, ok ? 16u : 0u);
+          }
+        }
+        cp_async_arrive_noinc(&full[slot]);
+        ++cnt;
+      }
+    }
+  } else if (warp == 4) {
+    // ================================ MMA ISSUER (whole warp, one elected lane) ================================
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t slab_u32 = smem_u32(s_slab), w_u32 = smem_u32(s_w);
+    constexpr uint32_t WSTEP = (uint32_t)NN * (W0 + W1);          // bytes of packed weights per (kd, kh) step
+    mbar_wait(wbar, 0);
+    const uint64_t bdesc0 = make_desc_kmajor_swz(w_u32, W0);
+    const uint64_t bdesc1 = make_desc_kmajor_swz(w_u32 + NN * W0, W1 ? W1 : 32);
+    uint32_t cnt_base = 0, acc_cnt = 0;
+    for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+      const int ch = (item / HW_tiles) % a.nchunks;
+      const int d0 = ch * a.dchunk, d1 = min(d0 + a.dchunk, a.D);
+      const int nd = d1 - d0;
+      for (int j = 0; j < nd; ++j) {
+        if (KD == 3) {
+          if (j == 0) for (int q = 0; q < 2; ++q) { uint32_t c = cnt_base + q; mbar_wait(&full[c % NSLOT], (c / NSLOT) & 1); }
+          uint32_t c = cnt_base + j + 2;
+          mbar_wait(&full[c % NSLOT], (c / NSLOT) & 1);
+        } else {
+          uint32_t c = cnt_base + j;
+          mbar_wait(&full[c % NSLOT], (c / NSLOT) & 1);
+        }
+        const uint32_t acc = acc_cnt % NACC;
+        mbar_wait(&tempty[acc], ((acc_cnt / NACC) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * (uint32_t)NN;
+        uint64_t adesc0_kd[KD], adesc1_kd[KD];
+#pragma unroll
+        for (int kd = 0; kd < KD; ++kd) {
+          const uint32_t sl = (cnt_base + j + kd) % NSLOT;
+          adesc0_kd[kd] = make_desc_kmajor_swz(slab_u32 + sl * slab_bytes, W0);
+          adesc1_kd[kd] = make_desc_kmajor_swz(slab_u32 + sl * slab_bytes + SLAB0, W1 ? W1 : 32);
+        }
+        if (elect_one()) {
+#pragma unroll
+          for (int kd = 0; kd < KD; ++kd) {
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+              {
+                const int st = kd * 3 + kh;
+#pragma unroll
+                for (int k = 0; k < G0 / 16; ++k) {      // start-address field is in 16-byte units: kh rows, 32 B per K step
+                  const uint64_t adesc = adesc0_kd[kd] + (uint64_t)((kh * WT * W0 + k * 32) >> 4);
+                  const uint64_t bdesc = bdesc0 + (uint64_t)((st * WSTEP + k * 32) >> 4);
+                  umma_f16(tmem_d, adesc, bdesc, idesc, (st | k) ? 1u : 0u);
+                }
+#pragma unroll
+                for (int k = 0; k < G1 / 16; ++k) {
+                  const uint64_t adesc = adesc1_kd[kd] + (uint64_t)((kh * WT * W1 + k * 32) >> 4);
+                  const uint64_t bdesc = bdesc1 + (uint64_t)((st * WSTEP + k * 32) >> 4);
+                  umma_f16(tmem_d, adesc, bdesc, idesc, 1u);
+                }
+              }
+            }
+          }
+          umma_commit(&tfull[acc]);
+          umma_commit(&empty[(cnt_base + j) % NSLOT]);
+        }
+        __syncwarp();
+        ++acc_cnt;
+      }
+      if (KD == 3) {
+        if (elect_one()) {
+          umma_commit(&empty[(cnt_base + nd) % NSLOT]);
+          umma_commit(&empty[(cnt_base + nd + 1) % NSLOT]);
+        }
+        __syncwarp();
+        cnt_base += nd + 2;
+      } else {
+        cnt_base += nd;
+      }
+    }
+  } else {
+    // ================================ EPILOGUE (2 groups x 4 warps; warp = tile row hh, lane = w') ==================
+    // Group g drains the tiles with (tile counter & 1) == g, so two tiles are in flight and the global-memory
+    // latencies of one (mask prefetch, stores) hide behind the other.
+    const int grp = warp >= 8 ? 1 : 0;
+    const int wq = warp & 3;
+    uint32_t acc_cnt = 0;
+    const size_t HWp = (size_t)a.H * a.W;
+    constexpr int NBR = COUT <= 32 ? COUT : 1;     // bias kept in registers for the (forward) layer widths
+    float biasr[NBR];
+#pragma unroll
+    for (int c = 0; c < NBR; ++c) biasr[c] = (a.bias && c < a.Cout) ? __ldg(a.bias + c) : 0.f;
+    auto bias_at = [&](int c) -> float { return COUT <= 32 ? biasr[COUT <= 32 ? c : 0] : (a.bias ? __ldg(a.bias + c) : 0.f); };
+    for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+      const int wt = item % a.tiles_w, ht = (item / a.tiles_w) % a.tiles_h;
+      const int ch = (item / HW_tiles) % a.nchunks, b = item / (HW_tiles * a.nchunks);
+      const int h = ht * HT + wq, w = wt * WUSE - 1 + lane, d0 = ch * a.dchunk, d1 = min(d0 + a.dchunk, a.D);
+      const bool valid = lane >= 1 && lane <= WUSE && h < a.H && w < a.W;
+      for (int d = d0; d < d1; ++d) {
+        if ((int)(acc_cnt & 1) != grp) { ++acc_cnt; continue; }
+        const uint32_t acc = acc_cnt % NACC;
+        const size_t vox = (((size_t)b * a.D + d) * a.H + h) * a.W + w;
+        // prefetch the LeakyReLU-derivative mask of this voxel before waiting for the tensor core
+        uint4 mreg[COUT / 8];
+        if (a.mask && valid) {
+#pragma unroll
+          for (int q = 0; q < COUT / 8; ++q)
+            if (q * 8 < a.Cout) mreg[q] = __ldg(reinterpret_cast<const uint4*>(a.mask + vox * a.Cout) + q);
+        }
+        mbar_wait(&tfull[acc], (acc_cnt / NACC) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * (uint32_t)NN;
+        const int c1 = a.out2 ? a.csplit : a.Cout;          // channels [0,c1) -> out, [c1,Cout) -> out2
+        // 16 output channels at a time: 3 x 16 TMEM columns (kw = 0,1,2), shuffle-combine across lanes, store
+#pragma unroll
+        for (int c0 = 0; c0 < COUT; c0 += 16) {
+          uint32_t r0[16], r1[16], r2[16];
+          tmem_ld16(taddr + c0, r0);
+          tmem_ld16(taddr + COUT + c0, r1);
+          tmem_ld16(taddr + 2 * COUT + c0, r2);
+          tmem_ld_wait();
+          if (c0 + 16 >= COUT) {          // last TMEM read of this accumulator
+            tc_fence_before();
+            mbar_arrive(&tempty[acc]);
+          }
+          float v[16];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const float p0 = __shfl_up_sync(0xffffffffu, __uint_as_float(r0[c]), 1);
+            const float p2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[c]), 1);
+            v[c] = (p0 + __uint_as_float(r1[c])) + p2;      // out[w'] = P0[w'-1] + P1[w'] + P2[w'+1]
+          }
+          if (valid && c0 < a.Cout) {
+            if (a.out_mode == 0) {
+#pragma unroll
+              for (int q = 0; q < 16; q += 8) {
+                if (c0 + q < a.Cout) {
+                  float x[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) x[e] = v[q + e] + bias_at(c0 + q + e);
+                  if (a.mask) {
+                    const uint4 m4 = mreg[(c0 + q) / 8];
+                    const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&m4);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) if (__bfloat162float(mb[e]) < 0.f) x[e] *= a.slope;
+                  } else if (a.slope >= 0.f) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) x[e] = x[e] >= 0.f ? x[e] : x[e] * a.slope;
+                  }
+                  // a split never falls inside a group of 8 channels (csplit % 8 == 0)
+                  const int cg = c0 + q;
+                  __nv_bfloat16* oo = cg < c1 ? reinterpret_cast<__nv_bfloat16*>(a.out) + vox * c1 + cg
+                                              : reinterpret_cast<__nv_bfloat16*>(a.out2) + vox * (a.Cout - c1) + (cg - c1);
+                  *reinterpret_cast<uint4*>(oo) = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+                }
+              }
+            } else {
+              float* o = reinterpret_cast<float*>(a.out);
+#pragma unroll
+              for (int c = 0; c < 16; ++c) {
+                if (c0 + c < a.Cout) {
+                  float x = v[c] + bias_at(c0 + c);
+                  if (a.slope >= 0.f) x = x >= 0.f ? x : x * a.slope;
+                  o[(((size_t)b * a.Cout + c0 + c) * a.D + d) * HWp + (size_t)h * a.W + w] = x;
+                }
+              }
+            }
+          }
+        }
+        ++acc_cnt;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// fp32 (Cout, Cin, KD, 3, 3) -> bf16, per (kd,kh) step two swizzled K-major tiles [N rows = kw*COUT + co][G0 ch] and [N][G1 ch]
+__global__ void pack_weights_s_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin, int KD, int COUT,
+                                      int NN, int G0, int G1, int transposed) {
+  const int T = KD * 9;
+  const int CG = G0 + G1;
+  const int total = KD * 3 * NN * CG;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ci = i % CG, n = (i / CG) % NN, st = i / (CG * NN);
+    const int kd = st / 3, kh = st % 3, g = n / COUT, co = n % COUT;
+    const int tap = (kd * 3 + kh) * 3 + g;
+    float v = 0.f;
+    if (!transposed) {
+      if (co < Cout && ci < Cin) v = w[((size_t)co * Cin + ci) * T + tap];
+    } else {
+      if (co < Cin && ci < Cout) v = w[((size_t)ci * Cin + co) * T + (T - 1 - tap)];
+    }
+    // destination: step tile = [group 0: NN x G0][group 1: NN x G1], bytes swizzled inside each group tile
+    const uint32_t W0 = G0 * 2, W1 = G1 * 2;
+    uint32_t off;
+    if (ci < G0) off = swz((uint32_t)n * W0 + (uint32_t)ci * 2u, W0);
+    else off = (uint32_t)NN * W0 + swz((uint32_t)n * W1 + (uint32_t)(ci - G0) * 2u, W1);
+    out[((size_t)st * NN * (W0 + W1) + off) / 2] = __float2bfloat16_rn(v);
+  }
+}
+
+// channel grouping of a convolution input of `cin` channels (8 counts as a zero-padded 16)
+static void groups_of(int cin, int* g0, int* g1) {
+  if (cin == 8 || cin == 16) { *g0 = 16; *g1 = 0; }
+  else if (cin == 32) { *g0 = 32; *g1 = 0; }
+  else if (cin == 48) { *g0 = 32; *g1 = 16; }
+  else { *g0 = 64; *g1 = 0; }
+}
+
+}  // namespace tcs
+}  // namespace vxm
+
+using namespace vxm;
+using namespace vxm::tcs;
+
+extern "C" size_t vxm_conv3d_tcs_packed_bytes(int cin_eff, int coutp, int kd) {
+  int g0, g1;
+  groups_of(cin_eff <= 8 ? 8 : (cin_eff <= 16 ? 16 : (cin_eff <= 32 ? 32 : (cin_eff <= 48 ? 48 : 64))), &g0, &g1);
+  return (size_t)kd * 3 * (3 * coutp) * (g0 + g1) * sizeof(__nv_bfloat16);
+}
+
+extern "C" int vxm_conv3d_tcs_pack(const float* w, void* wpk, int Cout, int Cin, int kd, int coutp, int transposed, void* stream) {
+  VXM_REQUIRE(w && wpk && Cout > 0 && Cin > 0 && (kd == 1 || kd == 3) && (coutp == 16 || coutp == 32 || coutp == 48 || coutp == 64), "conv3d_tcs_pack: bad argument");
+  int cin_eff = transposed ? Cout : Cin, nout = transposed ? Cin : Cout;
+  VXM_REQUIRE(nout <= coutp, "conv3d_tcs_pack: %d output channels do not fit %d", nout, coutp);
+  VXM_REQUIRE(cin_eff <= 64, "conv3d_tcs_pack: at most 64 input channels");
+  int g0, g1;
+  groups_of(cin_eff <= 8 ? 8 : (cin_eff <= 16 ? 16 : (cin_eff <= 32 ? 32 : (cin_eff <= 48 ? 48 : 64))), &g0, &g1);
+  int NN = 3 * coutp;
+  int total = kd * 3 * NN * (g0 + g1);
+  pack_weights_s_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(w, (__nv_bfloat16*)wpk, Cout, Cin, kd, coutp, NN, g0, g1, transposed);
+  return check_launch("conv3d_tcs_pack");
+}
+
+extern "C" int vxm_conv3d_tcs_supported(int Ca, int Cb, int Cout) {
+  int cin = Ca + Cb;
+  bool split_ok = cin != 48 || (Ca == 32 && Cb == 16) || Cb == 0 || Ca == 0;   // 48 = 32 + 16 channel groups
+  return (Cout <= 64) && (cin == 8 || cin == 16 || cin == 32 || cin == 48 || cin == 64) && Ca % 8 == 0 && Cb % 8 == 0 && split_ok;
+}
+
+extern "C" int vxm_conv3d_tcs_fwd(const void* xa, const void* xb, const void* wpk, const float* bias, void* out, const void* mask,
+                                  int B, int D, int H, int W, int Ca, int Cb, int up, int Cout, int coutp, int kd, int out_mode,
+                                  float slope, void* out2, int csplit, void* stream) {
+  VXM_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && wpk && out, "conv3d_tcs_fwd: bad argument");
+  VXM_REQUIRE(kd == 1 || kd == 3, "conv3d_tcs_fwd: kd must be 1 or 3");
+  VXM_REQUIRE(coutp == 16 || coutp == 32 || coutp == 48 || coutp == 64, "conv3d_tcs_fwd: padded Cout must be 16, 32, 48 or 64");
+  VXM_REQUIRE(!out2 || (out_mode == 0 && csplit > 0 && csplit < Cout && csplit % 8 == 0 && !mask), "conv3d_tcs_fwd: bad output split");
+  VXM_REQUIRE(Cout > 0 && Cout <= coutp && (out_mode == 1 || Cout % 8 == 0), "conv3d_tcs_fwd: unsupported Cout %d", Cout);
+  VXM_REQUIRE(vxm_conv3d_tcs_supported(Ca, Cb, Cout), "conv3d_tcs_fwd: channel counts (%d,%d)->%d unsupported", Ca, Cb, Cout);
+  VXM_REQUIRE((Ca == 0 || xa) && (Cb == 0 || xb), "conv3d_tcs_fwd: missing source tensor");
+  VXM_REQUIRE(!up || (H % 2 == 0 && W % 2 == 0 && (kd == 1 || D % 2 == 0)), "conv3d_tcs_fwd: upsampled source needs even sizes");
+  ConvSArgs a{};
+  const int cin = Ca + Cb;
+  int g0, g1;
+  groups_of(cin, &g0, &g1);
+  a.xa = (const __nv_bfloat16*)xa; a.xb = (const __nv_bfloat16*)xb; a.wpk = (const __nv_bfloat16*)wpk; a.bias = bias;
+  a.out = out; a.mask = (const __nv_bfloat16*)mask; a.out2 = out2; a.csplit = csplit;
+  a.B = B; a.D = D; a.H = H; a.W = W; a.Ca = Ca; a.Cb = Cb; a.up = up; a.upd = (up && kd == 3) ? 1 : 0;
+  a.Cout = Cout; a.out_mode = out_mode; a.slope = slope;
+  a.tiles_h = (H + HT - 1) / HT; a.tiles_w = (W + WUSE - 1) / WUSE;
+  int nsm = sm_count();
+  int dchunk = D;
+  auto items = [&](int dc) { return (long long)B * a.tiles_h * a.tiles_w * ((D + dc - 1) / dc); };
+  while (items(dchunk) < 4LL * nsm && dchunk > 8) dchunk = (dchunk + 1) / 2;
+  a.dchunk = dchunk; a.nchunks = (D + dchunk - 1) / dchunk;
+  a.nitems = (int)items(dchunk);
+  a.wbytes = (uint32_t)vxm_conv3d_tcs_packed_bytes(cin, coutp, kd);
+  const size_t slab = (size_t)SROWS * (g0 + g1) * 2;
+  VXM_REQUIRE((g0 + g1) / 8 * SROWS <= KMAX * NLOADER, "conv3d_tcs_fwd: slab too large for the loader table");
+  size_t fixed = ((a.wbytes + 1023u) & ~1023u) + 1024 + 512;
+  int nslot = (int)((227 * 1024 - fixed) / slab);
+  if (nslot > MAXSLOT) nslot = MAXSLOT;
+  VXM_REQUIRE(nslot >= 4, "conv3d_tcs_fwd: not enough shared memory for the slab ring");
+  a.nslot = nslot;
+  size_t smem = fixed + (size_t)nslot * slab;
+  int grid = a.nitems < nsm ? a.nitems : nsm;
+  cudaStream_t st = as_stream(stream);
+#define VXM_TCS_LAUNCH(KD_, G0_, G1_, CO_)                                                                                   \
+  do {                                                                                                                       \
+    VXM_CUDA(cudaFuncSetAttribute(conv_tcs_kernel<KD_, G0_, G1_, CO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    conv_tcs_kernel<KD_, G0_, G1_, CO_><<<grid, NTHREADS, smem, st>>>(a);                                                     \
+  } while (0)
+#define VXM_TCS_G(KD_, CO_)                                                   \
+  do {                                                                        \
+    if (g0 == 16) VXM_TCS_LAUNCH(KD_, 16, 0, CO_);                            \
+    else if (g0 == 32 && g1 == 0) VXM_TCS_LAUNCH(KD_, 32, 0, CO_);            \
+    else if (g0 == 32) VXM_TCS_LAUNCH(KD_, 32, 16, CO_);                      \
+    else VXM_TCS_LAUNCH(KD_, 64, 0, CO_);                                     \
+  } while (0)
+  if (kd == 3) { if (coutp == 16) VXM_TCS_G(3, 16); else if (coutp == 32) VXM_TCS_G(3, 32); else if (coutp == 48) VXM_TCS_G(3, 48); else VXM_TCS_G(3, 64); }
+  else { if (coutp == 16) VXM_TCS_G(1, 16); else if (coutp == 32) VXM_TCS_G(1, 32); else if (coutp == 48) VXM_TCS_G(1, 48); else VXM_TCS_G(1, 64); }
+  return check_launch("conv3d_tcs_fwd");
+}

@@ -140,16 +140,29 @@ def planar_to_ndhwc8(planes):
 
 # ---- weights-stationary ("transposed") kernel: Cin in {8,16,32,48}, Cout <= 32 -------------------------------------
 
-def use_t_kernel(ca, cb, cout):
-    """Kernel choice for one convolution launch: VXM_B200_TC_KERNEL = auto (default) | t | n."""
+def _variant():
+    """'s' = kw-stacked kernel with swizzled operands, 't' = kw-stacked with SWIZZLE_NONE operands, 'n' = one MMA per tap."""
     import os
-    mode = os.environ.get("VXM_B200_TC_KERNEL", "auto")
+    return os.environ.get("VXM_B200_TC_KERNEL", "auto")
+
+
+def use_t_kernel(ca, cb, cout):
+    """True when this convolution runs on a kw-stacked kernel (VXM_B200_TC_KERNEL = auto | s | t | n)."""
+    mode = _variant()
     if mode == "n":
         return False
-    return bool(_lib.load().vxm_conv3d_tct_supported(ca, cb, cout))
+    lib = _lib.load()
+    if mode in ("auto", "s") and lib.vxm_conv3d_tcs_supported(ca, cb, cout):
+        return True
+    return bool(lib.vxm_conv3d_tct_supported(ca, cb, cout))
 
 
-def pack_weights_t(w, transposed=False):
+def _use_s(ca, cb, cout):
+    return _variant() in ("auto", "s") and bool(_lib.load().vxm_conv3d_tcs_supported(ca, cb, cout))
+
+
+def pack_weights_t(w, transposed=False, variant=None):
+    """Packed weights for a kw-stacked kernel.  Returns (tensor, (coutp, variant))."""
     lib = _lib.load()
     if w.dim() == 4:
         w = w.unsqueeze(2)
@@ -157,15 +170,21 @@ def pack_weights_t(w, transposed=False):
     Cout, Cin, kd = w.shape[0], w.shape[1], w.shape[2]
     cin_eff, nout = (Cout, Cin) if transposed else (Cin, Cout)
     coutp = 16 if nout <= 16 else (32 if nout <= 32 else (48 if nout <= 48 else 64))
-    nbytes = int(lib.vxm_conv3d_tct_packed_bytes(cin_eff, coutp, kd))
+    if variant is None:
+        variant = "s" if _variant() in ("auto", "s") else "t"
+    fb, fp = (lib.vxm_conv3d_tcs_packed_bytes, lib.vxm_conv3d_tcs_pack) if variant == "s" else \
+             (lib.vxm_conv3d_tct_packed_bytes, lib.vxm_conv3d_tct_pack)
+    nbytes = int(fb(cin_eff, coutp, kd))
     out = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
-    _lib.check(lib.vxm_conv3d_tct_pack(_lib.ptr(w), _lib.ptr(out), Cout, Cin, kd, coutp, 1 if transposed else 0,
-                                       _lib.stream_ptr()), "vxm_conv3d_tct_pack")
-    return out, coutp
+    _lib.check(fp(_lib.ptr(w), _lib.ptr(out), Cout, Cin, kd, coutp, 1 if transposed else 0, _lib.stream_ptr()),
+               "vxm_conv3d_tc%s_pack" % variant)
+    return out, (coutp, variant)
 
 
 def conv_fwd_t(xa, xb, wpk, coutp, bias, cout, kd, up=False, out_fp32_planar=False, slope=None, mask=None, split=None):
     lib = _lib.load()
+    coutp, variant = coutp if isinstance(coutp, tuple) else (coutp, "t")
+    fwd = lib.vxm_conv3d_tcs_fwd if variant == "s" else lib.vxm_conv3d_tct_fwd
     full = xb if xb is not None else xa
     B, D, H, W = full.shape[0], full.shape[1], full.shape[2], full.shape[3]
     if xb is None and up:
@@ -182,7 +201,7 @@ def conv_fwd_t(xa, xb, wpk, coutp, bias, cout, kd, up=False, out_fp32_planar=Fal
     else:
         out = torch.empty((B, D, H, W, cout), dtype=torch.bfloat16, device=dev)
     s = -1.0 if slope is None else float(slope)
-    _lib.check(lib.vxm_conv3d_tct_fwd(_lib.ptr(xa), _lib.ptr(xb), _lib.ptr(wpk), _lib.ptr(bias), _lib.ptr(out), _lib.ptr(mask),
-                                      B, D, H, W, Ca, Cb, 1 if up else 0, cout, coutp, kd, 1 if out_fp32_planar else 0, s,
-                                      _lib.ptr(out2), int(split or 0), _lib.stream_ptr()), "vxm_conv3d_tct_fwd")
+    _lib.check(fwd(_lib.ptr(xa), _lib.ptr(xb), _lib.ptr(wpk), _lib.ptr(bias), _lib.ptr(out), _lib.ptr(mask),
+                   B, D, H, W, Ca, Cb, 1 if up else 0, cout, coutp, kd, 1 if out_fp32_planar else 0, s,
+                   _lib.ptr(out2), int(split or 0), _lib.stream_ptr()), "vxm_conv3d_tc%s_fwd" % variant)
     return (out, out2) if split else out
