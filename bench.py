@@ -388,8 +388,16 @@ def b200_arm(args):
     _, flops_step = conv_flops_per_step(shape)
     ach = flops_step / (conv_total_ms * 1e-3) / 1e12
     engine = ops.conv_engine()
+    # DRAM traffic of the conv family per step: taken from the committed ncu pass over this same command
+    # (profiles/r1_traffic.json; ncu cannot run inside a timed bench), valid for the full-size bf16 workload only.
+    traffic, traffic_src = None, None
+    tj = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")
+    if engine == "bf16" and tuple(shape) == (160, 192, 224) and os.path.exists(tj):
+        with open(tj) as f:
+            tinfo = json.load(f)
+        traffic, traffic_src = tinfo["conv_dram_mbytes_per_step"] * 1e6, tinfo["source"]
     roofline = dict(bound="tensor", kernel="conv3d k3 fwd+dgrad+wgrad, all 12 layers (%s)" % ("tcgen05 bf16 implicit GEMM" if engine == "bf16" else "fp32 FFMA engine"),
-                    achieved=ach, peak=peaks["tf_sus"], unit="TFLOP/s", frac=ach / peaks["tf_sus"], traffic=None,
+                    achieved=ach, peak=peaks["tf_sus"], unit="TFLOP/s", frac=ach / peaks["tf_sus"], traffic=traffic, traffic_unit="bytes per step (all conv launches)", traffic_source=traffic_src,
                     peak_source=peaks["source"] + ", sustained bf16", ms_per_step=conv_total_ms, conv_launches=n_conv_launches,
                     share_of_step=conv_total_ms / (ms / K), flops_per_step=flops_step)
 

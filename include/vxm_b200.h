@@ -177,13 +177,13 @@ int vxm_conv3d_tcs_fwd(const void* xa, const void* xb, const void* wpk, const fl
 /* Weight (and bias) gradient on tensor cores.  x sources as in vxm_conv3d_tc_fwd (the layer's forward input);
  * gz = gradient w.r.t. the convolution output (already multiplied by the activation derivative): bf16 NDHWC with
  * Cg in {8,16,32} channels, or nplanar_g (<= 4) planar fp32 volumes (flow head).  grad_w: fp32
- * (Cout_real, Cin_real, kd, 3, 3), overwritten; grad_b: fp32 (Cout_real), overwritten, may be NULL (and must be
- * NULL for planar gz).  work: vxm_conv3d_tc_wgrad_workspace_bytes(kd). */
+ * (Cout_real, Cin_real, kd, 3, 3); grad_b: fp32 (Cout_real), may be NULL.  accumulate = 0 overwrites them, 1 adds to
+ * them (gradient buffers zeroed once per step).  work: vxm_conv3d_tc_wgrad_workspace_bytes(kd). */
 size_t vxm_conv3d_tc_wgrad_workspace_bytes(int kd);
 int vxm_conv3d_tc_wgrad(const void* xa, const void* xb, const float* const* xf, const long long* xf_bstride,
                         int nplanar_x, const void* gz, const float* const* gf, const long long* gf_bstride,
                         int nplanar_g, float* grad_w, float* grad_b, void* work, int B, int D, int H, int W,
-                        int Ca, int Cb, int up, int Cin_real, int Cg, int Cout_real, int kd, void* stream);
+                        int Ca, int Cb, int up, int Cin_real, int Cg, int Cout_real, int kd, int accumulate, void* stream);
 /* ---- channels-last bf16 glue of the tensor-core U-Net engine (reference networks.py:126-138 and its autograd) ----
  * All tensors bf16 (B,D,H,W,C), C % 8 == 0.  (Dc,Hc,Wc) are the COARSE dims; the fine tensor is (fd*Dc, 2Hc, 2Wc)
  * with fd = 2 for nd == 3 and 1 for nd == 2. */

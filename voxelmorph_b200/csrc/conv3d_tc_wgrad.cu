@@ -411,20 +411,23 @@ __global__ void __launch_bounds__(WNTHREADS, 1) wgrad_tc_kernel(const WgradTcArg
   }
 }
 
-// gw[co][ci][tap] = sum_cta partial[cta][tap][ci][co]   (fixed order -> deterministic)
+// gw[co][ci][tap] (+)= sum_cta partial[cta][tap][ci][co]   (fixed order -> deterministic).  Threads walk the partial
+// layout (co fastest) so the ncta reads per element are coalesced; the small transposed write is scattered.
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ gw, int ncta, int T, int NP, int Cout, int Cin,
-                                    const float* __restrict__ bias_partial, float* __restrict__ gb) {
-  const int total = Cout * Cin * T;
+                                    const float* __restrict__ bias_partial, float* __restrict__ gb, int accumulate) {
   if (gb && blockIdx.x == 0 && threadIdx.x < Cout) {
-    float acc = 0.f;
+    float acc = accumulate ? gb[threadIdx.x] : 0.f;
     for (int c = 0; c < ncta; ++c) acc += bias_partial[(size_t)c * NP + threadIdx.x];
     gb[threadIdx.x] = acc;
   }
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int tap = i % T, ci = (i / T) % Cin, co = i / (T * Cin);
+  const int per_cta = T * 64 * NP;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < per_cta; j += gridDim.x * blockDim.x) {
+    const int co = j % NP, ci = (j / NP) % 64, tap = j / (NP * 64);
+    if (co >= Cout || ci >= Cin) continue;
     float acc = 0.f;
-    for (int c = 0; c < ncta; ++c) acc += partial[(((size_t)c * T + tap) * 64 + ci) * NP + co];
-    gw[i] = acc;
+    for (int c = 0; c < ncta; ++c) acc += partial[(size_t)c * per_cta + j];
+    float* dst = gw + ((size_t)co * Cin + ci) * T + tap;
+    *dst = (accumulate ? *dst : 0.f) + acc;
   }
 }
 
@@ -468,7 +471,7 @@ extern "C" size_t vxm_conv3d_tc_wgrad_workspace_bytes(int kd) {
 extern "C" int vxm_conv3d_tc_wgrad(const void* xa, const void* xb, const float* const* xf, const long long* xf_bs, int nplanar_x,
                                    const void* gz, const float* const* gf, const long long* gf_bs, int nplanar_g,
                                    float* grad_w, float* grad_b, void* work, int B, int D, int H, int W, int Ca, int Cb, int up,
-                                   int Cin_real, int Cg, int Cout_real, int kd, void* stream) {
+                                   int Cin_real, int Cg, int Cout_real, int kd, int accumulate, void* stream) {
   VXM_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && grad_w && work, "conv3d_tc_wgrad: bad argument");
   VXM_REQUIRE(kd == 1 || kd == 3, "conv3d_tc_wgrad: kd must be 1 or 3");
   WgradTcArgs a{};
@@ -533,7 +536,8 @@ extern "C" int vxm_conv3d_tc_wgrad(const void* xa, const void* xb, const float* 
   int rc = check_launch("conv3d_tc_wgrad");
   if (rc) return rc;
   int T = kd * 9;
-  int total = Cout_real * Cin_real * T;
-  wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(a.partial, grad_w, grid, T, a.NP, Cout_real, Cin_real, a.bias_partial, grad_b);
+  int per_cta = T * 64 * a.NP;
+  wgrad_reduce_kernel<<<(per_cta + 255) / 256, 256, 0, st>>>(a.partial, grad_w, grid, T, a.NP, Cout_real, Cin_real, a.bias_partial, grad_b,
+                                                             accumulate);
   return check_launch("conv3d_tc_wgrad_reduce");
 }

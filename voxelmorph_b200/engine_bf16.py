@@ -212,11 +212,19 @@ def backward_tape(ctx, g_flow):
             g_in = tc.planar_to_ndhwc8([g_flow[:, i:i + 1] for i in range(g_flow.shape[1])])
         else:
             g_in = gz.pop(cv.out_id)
-        gw, gb = tc.conv_wgrad(cv.xa, cv.xb, g_in, cv.cin, cv.cout, kd, up=cv.up, planar_x=cv.planar)
+        # parameters whose .grad is a view of FusedAdam's flat gradient buffer (optim.FlatParams marks them)
+        # are accumulated into directly by the reduce kernel; autograd then receives no gradient for them
+        direct = (getattr(cv.w, "_vxm_flat_grad", False) and cv.w.grad is not None and cv.w.grad.is_contiguous()
+                  and (cv.b is None or (getattr(cv.b, "_vxm_flat_grad", False) and cv.b.grad is not None)))
+        if direct:
+            tc.conv_wgrad(cv.xa, cv.xb, g_in, cv.cin, cv.cout, kd, up=cv.up, planar_x=cv.planar,
+                          out_w=cv.w.grad, out_b=None if cv.b is None else cv.b.grad)
+        else:
+            gw, gb = tc.conv_wgrad(cv.xa, cv.xb, g_in, cv.cin, cv.cout, kd, up=cv.up, planar_x=cv.planar)
+            grads[cv.w] = gw.squeeze(2) if nd == 2 else gw
+            if cv.b is not None:
+                grads[cv.b] = gb
         g_in_planar = None
-        grads[cv.w] = gw.squeeze(2) if nd == 2 else gw
-        if cv.b is not None:
-            grads[cv.b] = gb
         # ---- dgrad ----
         if cv.planar is not None or producer.get(cv.a_id) == "input":
             continue       # first layer: the images need no gradient

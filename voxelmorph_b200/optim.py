@@ -30,6 +30,7 @@ class FlatParams:
                 self.flat[off:off + k].copy_(p.data.reshape(-1))
                 p.data = self.flat[off:off + k].view_as(p)
                 p.grad = self.grad[off:off + k].view_as(p)
+                p._vxm_flat_grad = True     # engine_bf16 accumulates weight gradients straight into this view
                 off += k
 
     def zero_grad(self):

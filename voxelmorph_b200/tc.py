@@ -97,7 +97,7 @@ def _planar_args(planar):
 _wgrad_ws = {}
 
 
-def conv_wgrad(xa, xb, gz, cin, cout, kd, up=False, planar_x=None, planar_g=None, need_bias=True):
+def conv_wgrad(xa, xb, gz, cin, cout, kd, up=False, planar_x=None, planar_g=None, need_bias=True, out_w=None, out_b=None):
     """fp32 grad_w (cout, cin, kd, 3, 3) and grad_b (cout) from the layer input (xa/xb or planar_x) and gz."""
     lib = _lib.load()
     ref = gz if gz is not None else planar_g[0]
@@ -111,15 +111,17 @@ def conv_wgrad(xa, xb, gz, cin, cout, kd, up=False, planar_x=None, planar_g=None
     if work is None:
         work = torch.empty(int(lib.vxm_conv3d_tc_wgrad_workspace_bytes(kd)), dtype=torch.uint8, device=dev)
         _wgrad_ws[key] = work
-    gw = torch.empty((cout, cin, kd, 3, 3), dtype=torch.float32, device=dev)
-    gb = torch.empty(cout, dtype=torch.float32, device=dev) if need_bias else None
+    # out_w / out_b: existing (contiguous fp32) gradient buffers to ACCUMULATE into instead of fresh tensors
+    accumulate = out_w is not None
+    gw = out_w if accumulate else torch.empty((cout, cin, kd, 3, 3), dtype=torch.float32, device=dev)
+    gb = out_b if accumulate else (torch.empty(cout, dtype=torch.float32, device=dev) if need_bias else None)
     xf, xs, npx = _planar_args(planar_x)
     gf, gs, npg = _planar_args(planar_g)
     Ca = 0 if xa is None else xa.shape[-1]
     Cb = 0 if xb is None else xb.shape[-1]
     _lib.check(lib.vxm_conv3d_tc_wgrad(_lib.ptr(xa), _lib.ptr(xb), xf, xs, npx, _lib.ptr(gz), gf, gs, npg, _lib.ptr(gw),
                                        _lib.ptr(gb), _lib.ptr(work), B, D, H, W, Ca, Cb, 1 if up else 0, cin, Cg, cout, kd,
-                                       _lib.stream_ptr()), "vxm_conv3d_tc_wgrad")
+                                       1 if accumulate else 0, _lib.stream_ptr()), "vxm_conv3d_tc_wgrad")
     return gw, gb
 
 
