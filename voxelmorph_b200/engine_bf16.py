@@ -21,16 +21,20 @@ def bump_weights_epoch():
 
 
 class _PackCache:
-    def __init__(self):
-        self.c = {}
+    """Packed (bf16, MMA-ordered) copies of the convolution weights.  The copies live ON the parameter object
+    (attribute `_vxm_packs`), so they die with it: a table keyed by id()/data_ptr would hand a new model the packed
+    weights of a freed one whenever Python and the caching allocator both reuse the address."""
 
     def get(self, w, key, fn):
-        k = (id(w), key)
-        stamp = (w.data_ptr(), w._version, _weights_epoch)
-        hit = self.c.get(k)
+        packs = getattr(w, "_vxm_packs", None)
+        if packs is None:
+            packs = {}
+            w._vxm_packs = packs
+        stamp = (w.data_ptr(), w._version, _weights_epoch, tuple(w.shape), tc._variant())
+        hit = packs.get(key)
         if hit is None or hit[0] != stamp:
             hit = (stamp, fn())
-            self.c[k] = hit
+            packs[key] = hit
         return hit[1]
 
 
