@@ -461,6 +461,14 @@ __global__ void bias_grad_final_kernel(const float* __restrict__ part, float* __
 using namespace vxm;
 using namespace vxm::tc;
 
+namespace vxm {
+namespace tcw {   // conv3d_tc_wgrad2.cu: the kw-stacked Toeplitz formulation (channels-last bf16 sources only)
+bool wgrad2_supported(int Ca, int Cb, int Cg);
+int wgrad2_launch(const void* x, int Cx, int up, const void* gz, int Cg, float* grad_w, float* grad_b, void* work, int B, int D, int H, int W,
+                  int kd, int Cout_real, int Cin_total, int ci_off, int ci_cnt, int accumulate, cudaStream_t st);
+}
+}
+
 static int wgrad_np(int cg) { return cg <= 8 ? 8 : cg <= 16 ? 16 : 32; }
 
 extern "C" size_t vxm_conv3d_tc_wgrad_workspace_bytes(int kd) {
@@ -496,6 +504,21 @@ extern "C" int vxm_conv3d_tc_wgrad(const void* xa, const void* xb, const float* 
     VXM_REQUIRE(gz && Cg % 8 == 0 && Cg >= 8 && Cg <= 32, "conv3d_tc_wgrad: gz channels %d unsupported", Cg);
   }
   VXM_REQUIRE(Cout_real > 0 && Cout_real <= Cg, "conv3d_tc_wgrad: Cout_real out of range");
+  if (nplanar_x == 0 && nplanar_g == 0 && tcw::wgrad2_supported(Ca, Cb, Cg)) {
+    // one launch per source tensor of the (virtual) concatenation: xa -> weights [0, Ca), xb -> [Ca, Ca + Cb)
+    cudaStream_t st2 = as_stream(stream);
+    int rc = 0;
+    if (Ca) {
+      const int cnt = Cin_real < Ca ? Cin_real : Ca;
+      rc = tcw::wgrad2_launch(xa, Ca, up, gz, Cg, grad_w, grad_b, work, B, D, H, W, kd, Cout_real, Cin_real, 0, cnt, accumulate, st2);
+      if (rc) return rc;
+    }
+    if (Cb && Cin_real > Ca) {
+      const int cnt = Cin_real - Ca < Cb ? Cin_real - Ca : Cb;
+      rc = tcw::wgrad2_launch(xb, Cb, 0, gz, Cg, grad_w, Ca ? nullptr : grad_b, work, B, D, H, W, kd, Cout_real, Cin_real, Ca, cnt, accumulate, st2);
+    }
+    return rc;
+  }
   a.xa = (const __nv_bfloat16*)xa; a.xb = (const __nv_bfloat16*)xb; a.gz = (const __nv_bfloat16*)gz;
   a.Ca = Ca; a.Cb = Cb; a.up = up; a.upd = (up && kd == 3) ? 1 : 0; a.Cg = Cg;
   a.B = B; a.D = D; a.H = H; a.W = W; a.KD = kd; a.NP = wgrad_np(Cg);
