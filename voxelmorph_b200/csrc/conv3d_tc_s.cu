@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const ConvSArgs a
   if (warp >= 5 && warp < 8) {
     // ================================ LOADER (96 threads) ================================
     const int lt = threadIdx.x - 5 * 32;
-    uint32_t cnt = 0;
+    uint32_t slot = 0, lphase = 1;   // producer side: the first lap passes on the fresh barriers
     const int Da = a.upd ? a.D >> 1 : a.D, Ha = a.up ? a.H >> 1 : a.H, Wa = a.up ? a.W >> 1 : a.W;
     const int nca8 = a.Ca >> 3;
     constexpr int nchunk = NC8 * SROWS;
@@ -122,8 +122,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const ConvSArgs a
         }
       }
       for (int ds = s_begin; ds < s_end; ++ds) {
-        const int slot = cnt % NSLOT;
-        mbar_wait(&empty[slot], ((cnt / NSLOT) & 1) ^ 1);
+        mbar_wait(&empty[slot], lphase);
         uint8_t* slab = s_slab + (size_t)slot * slab_bytes;
         const bool dok = ds >= 0 && ds < a.D;
         const __nv_bfloat16* baseA = a.xa ? a.xa + (((size_t)b * Da + (dok ? (a.upd ? ds >> 1 : ds) : 0)) * Ha * Wa) * a.Ca : nullptr;
@@ -138,7 +137,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const ConvSArgs a
           }
         }
         cp_async_arrive_noinc(&full[slot]);
-        ++cnt;
+        if (++slot == (uint32_t)NSLOT) { slot = 0; lphase ^= 1; }
       }
     }
   } else if (warp == 4) {
@@ -149,30 +148,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const ConvSArgs a
     mbar_wait(wbar, 0);
     const uint64_t bdesc0 = make_desc_kmajor_swz(w_u32, W0);
     const uint64_t bdesc1 = make_desc_kmajor_swz(w_u32 + NN * W0, W1 ? W1 : 32);
-    uint32_t cnt_base = 0, acc_cnt = 0;
+    // slot / phase bookkeeping is incremental (no runtime modulo: the issue loop is the critical path of the thin layers)
+    uint32_t wslot = 0, wphase = 0;     // next slab to wait for
+    uint32_t hslot = 0;                 // head of the kd window
+    uint32_t acc = 0, aphase = 1;       // accumulator ring (consumer of tempty: first lap passes)
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
       const int ch = (item / HW_tiles) % a.nchunks;
       const int d0 = ch * a.dchunk, d1 = min(d0 + a.dchunk, a.D);
       const int nd = d1 - d0;
       for (int j = 0; j < nd; ++j) {
-        if (KD == 3) {
-          if (j == 0) for (int q = 0; q < 2; ++q) { uint32_t c = cnt_base + q; mbar_wait(&full[c % NSLOT], (c / NSLOT) & 1); }
-          uint32_t c = cnt_base + j + 2;
-          mbar_wait(&full[c % NSLOT], (c / NSLOT) & 1);
-        } else {
-          uint32_t c = cnt_base + j;
-          mbar_wait(&full[c % NSLOT], (c / NSLOT) & 1);
+        const int nwait = (KD == 3 && j == 0) ? 3 : 1;
+        for (int q = 0; q < nwait; ++q) {
+          mbar_wait(&full[wslot], wphase);
+          if (++wslot == (uint32_t)NSLOT) { wslot = 0; wphase ^= 1; }
         }
-        const uint32_t acc = acc_cnt % NACC;
-        mbar_wait(&tempty[acc], ((acc_cnt / NACC) & 1) ^ 1);
+        mbar_wait(&tempty[acc], aphase);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * (uint32_t)NN;
         uint64_t adesc0_kd[KD], adesc1_kd[KD];
+        {
+          uint32_t sl = hslot;
 #pragma unroll
-        for (int kd = 0; kd < KD; ++kd) {
-          const uint32_t sl = (cnt_base + j + kd) % NSLOT;
-          adesc0_kd[kd] = make_desc_kmajor_swz(slab_u32 + sl * slab_bytes, W0);
-          adesc1_kd[kd] = make_desc_kmajor_swz(slab_u32 + sl * slab_bytes + SLAB0, W1 ? W1 : 32);
+          for (int kd = 0; kd < KD; ++kd) {
+            adesc0_kd[kd] = make_desc_kmajor_swz(slab_u32 + sl * slab_bytes, W0);
+            adesc1_kd[kd] = make_desc_kmajor_swz(slab_u32 + sl * slab_bytes + SLAB0, W1 ? W1 : 32);
+            if (++sl == (uint32_t)NSLOT) sl = 0;
+          }
         }
         if (elect_one()) {
 #pragma unroll
@@ -197,20 +198,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const ConvSArgs a
             }
           }
           umma_commit(&tfull[acc]);
-          umma_commit(&empty[(cnt_base + j) % NSLOT]);
+          umma_commit(&empty[hslot]);
         }
         __syncwarp();
-        ++acc_cnt;
+        if (++acc == (uint32_t)NACC) { acc = 0; aphase ^= 1; }
+        if (++hslot == (uint32_t)NSLOT) hslot = 0;
       }
       if (KD == 3) {
+        const uint32_t h1 = hslot + 1 == (uint32_t)NSLOT ? 0 : hslot + 1;
         if (elect_one()) {
-          umma_commit(&empty[(cnt_base + nd) % NSLOT]);
-          umma_commit(&empty[(cnt_base + nd + 1) % NSLOT]);
+          umma_commit(&empty[hslot]);
+          umma_commit(&empty[h1]);
         }
         __syncwarp();
-        cnt_base += nd + 2;
-      } else {
-        cnt_base += nd;
+        hslot = h1 + 1 == (uint32_t)NSLOT ? 0 : h1 + 1;
       }
     }
   } else {
