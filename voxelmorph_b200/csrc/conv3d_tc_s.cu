@@ -15,9 +15,8 @@ namespace tcs {
 
 using namespace vxm::tc;
 
-constexpr int HT = 4, WT = 32, WUSE = 30;
-constexpr int SROWS = (HT + 2) * WT;   // 192 voxels (rows) per slab
-constexpr int MAXSLOT = 8, MAXACC = 4, KMAX = 16;
+constexpr int WT = 32, WUSE = 30;      // tile: HT (4 or 8) rows x 32 columns (30 written), slab = (HT + 2) x 32 voxel rows
+constexpr int MAXSLOT = 8, MAXACC = 4;
 constexpr int NLOADER = 96, NTHREADS = 384;   // warps 0-3 epilogue group 0, 4 MMA issuer, 5-7 loader, 8-11 epilogue group 1
 
 struct ConvSArgs {
@@ -45,8 +44,12 @@ __device__ __forceinline__ uint64_t make_desc_kmajor_swz(uint32_t saddr, uint32_
   return d;
 }
 
-template <int KD, int G0, int G1, int COUT>
+// HT = 8: one slab step feeds TWO 4-row accumulators (one per epilogue group), halving the per-step issue / barrier
+// overhead that bounds the thin layers and cutting the halo re-reads from 1.5x to 1.25x.
+template <int KD, int G0, int G1, int COUT, int HT>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const ConvSArgs a) {
+  constexpr int SROWS = (HT + 2) * WT;
+  constexpr int NH = HT / 4;
   constexpr int W0 = G0 * 2, W1 = G1 * 2;                 // row bytes of the two channel groups
   constexpr int NC8 = (G0 + G1) / 8;                      // 16-byte chunks per voxel
   constexpr uint32_t SLAB0 = SROWS * W0, SLAB1 = SROWS * W1;
@@ -97,6 +100,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const ConvSArgs a
     const int Da = a.upd ? a.D >> 1 : a.D, Ha = a.up ? a.H >> 1 : a.H, Wa = a.up ? a.W >> 1 : a.W;
     const int nca8 = a.Ca >> 3;
     constexpr int nchunk = NC8 * SROWS;
+    constexpr int KMAX = (nchunk + NLOADER - 1) / NLOADER;
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
       const int wt = item % a.tiles_w, ht = (item / a.tiles_w) % a.tiles_h;
       const int ch = (item / HW_tiles) % a.nchunks, b = item / (HW_tiles * a.nchunks);
@@ -162,9 +166,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const ConvSArgs a
           mbar_wait(&full[wslot], wphase);
           if (++wslot == (uint32_t)NSLOT) { wslot = 0; wphase ^= 1; }
         }
-        mbar_wait(&tempty[acc], aphase);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * (uint32_t)NN;
         uint64_t adesc0_kd[KD], adesc1_kd[KD];
         {
           uint32_t sl = hslot;
@@ -175,6 +176,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const ConvSArgs a
             if (++sl == (uint32_t)NSLOT) sl = 0;
           }
         }
+#pragma unroll
+        for (int hb = 0; hb < NH; ++hb) {
+        mbar_wait(&tempty[acc], aphase);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * (uint32_t)NN;
         if (elect_one()) {
 #pragma unroll
           for (int kd = 0; kd < KD; ++kd) {
@@ -184,13 +190,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const ConvSArgs a
                 const int st = kd * 3 + kh;
 #pragma unroll
                 for (int k = 0; k < G0 / 16; ++k) {      // start-address field is in 16-byte units: kh rows, 32 B per K step
-                  const uint64_t adesc = adesc0_kd[kd] + (uint64_t)((kh * WT * W0 + k * 32) >> 4);
+                  const uint64_t adesc = adesc0_kd[kd] + (uint64_t)(((hb * 4 + kh) * WT * W0 + k * 32) >> 4);
                   const uint64_t bdesc = bdesc0 + (uint64_t)((st * WSTEP + k * 32) >> 4);
                   umma_f16(tmem_d, adesc, bdesc, idesc, (st | k) ? 1u : 0u);
                 }
 #pragma unroll
                 for (int k = 0; k < G1 / 16; ++k) {
-                  const uint64_t adesc = adesc1_kd[kd] + (uint64_t)((kh * WT * W1 + k * 32) >> 4);
+                  const uint64_t adesc = adesc1_kd[kd] + (uint64_t)(((hb * 4 + kh) * WT * W1 + k * 32) >> 4);
                   const uint64_t bdesc = bdesc1 + (uint64_t)((st * WSTEP + k * 32) >> 4);
                   umma_f16(tmem_d, adesc, bdesc, idesc, 1u);
                 }
@@ -198,10 +204,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const ConvSArgs a
             }
           }
           umma_commit(&tfull[acc]);
-          umma_commit(&empty[hslot]);
+          if (hb == NH - 1) umma_commit(&empty[hslot]);
         }
         __syncwarp();
         if (++acc == (uint32_t)NACC) { acc = 0; aphase ^= 1; }
+        }
         if (++hslot == (uint32_t)NSLOT) hslot = 0;
       }
       if (KD == 3) {
@@ -230,10 +237,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const ConvSArgs a
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
       const int wt = item % a.tiles_w, ht = (item / a.tiles_w) % a.tiles_h;
       const int ch = (item / HW_tiles) % a.nchunks, b = item / (HW_tiles * a.nchunks);
-      const int h = ht * HT + wq, w = wt * WUSE - 1 + lane, d0 = ch * a.dchunk, d1 = min(d0 + a.dchunk, a.D);
-      const bool valid = lane >= 1 && lane <= WUSE && h < a.H && w < a.W;
+      const int w = wt * WUSE - 1 + lane, d0 = ch * a.dchunk, d1 = min(d0 + a.dchunk, a.D);
       for (int d = d0; d < d1; ++d) {
+#pragma unroll
+        for (int hb = 0; hb < NH; ++hb) {
         if ((int)(acc_cnt & 1) != grp) { ++acc_cnt; continue; }
+        const int h = ht * HT + hb * 4 + wq;
+        const bool valid = lane >= 1 && lane <= WUSE && h < a.H && w < a.W;
         const uint32_t acc = acc_cnt % NACC;
         const size_t vox = (((size_t)b * a.D + d) * a.H + h) * a.W + w;
         // prefetch the LeakyReLU-derivative mask of this voxel before waiting for the tensor core
@@ -304,6 +314,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const ConvSArgs a
           }
         }
         ++acc_cnt;
+        }
       }
     }
   }
@@ -398,17 +409,32 @@ extern "C" int vxm_conv3d_tcs_fwd(const void* xa, const void* xb, const void* wp
   a.out = out; a.mask = (const __nv_bfloat16*)mask; a.out2 = out2; a.csplit = csplit;
   a.B = B; a.D = D; a.H = H; a.W = W; a.Ca = Ca; a.Cb = Cb; a.up = up; a.upd = (up && kd == 3) ? 1 : 0;
   a.Cout = Cout; a.out_mode = out_mode; a.slope = slope;
-  a.tiles_h = (H + HT - 1) / HT; a.tiles_w = (W + WUSE - 1) / WUSE;
-  int nsm = sm_count();
-  int dchunk = D;
-  auto items = [&](int dc) { return (long long)B * a.tiles_h * a.tiles_w * ((D + dc - 1) / dc); };
-  while (items(dchunk) < 4LL * nsm && dchunk > 8) dchunk = (dchunk + 1) / 2;
-  a.dchunk = dchunk; a.nchunks = (D + dchunk - 1) / dchunk;
-  a.nitems = (int)items(dchunk);
   a.wbytes = (uint32_t)vxm_conv3d_tcs_packed_bytes(cin, coutp, kd);
-  const size_t slab = (size_t)SROWS * (g0 + g1) * 2;
-  VXM_REQUIRE((g0 + g1) / 8 * SROWS <= KMAX * NLOADER, "conv3d_tcs_fwd: slab too large for the loader table");
-  size_t fixed = ((a.wbytes + 1023u) & ~1023u) + 1024 + 512;
+  const size_t fixed = ((a.wbytes + 1023u) & ~1023u) + 1024 + 512;
+  // tile height: 8 rows (two accumulators per slab step) when the ring still holds >= 5 slabs and 4 accumulators fit TMEM
+  int HTv = 4;
+  {
+    const size_t slab8 = (size_t)10 * WT * (g0 + g1) * 2;
+    const int ns8 = (int)((227 * 1024 - fixed) / slab8);
+    const char* e = getenv("VXM_B200_TCS_HT");
+    if (g0 <= 32 && coutp <= 32 && ns8 >= (kd == 3 ? 5 : 3) && H > 4 && !(e && e[0] == '4')) HTv = 8;
+  }
+  a.tiles_h = (H + HTv - 1) / HTv; a.tiles_w = (W + WUSE - 1) / WUSE;
+  int nsm = sm_count();
+  // depth chunking: balance the persistent CTAs (waves of nsm items) against the 2 halo slabs every chunk re-loads
+  const long long tiles = (long long)B * a.tiles_h * a.tiles_w;
+  int best_nch = 1;
+  double best_cost = 1e300;
+  for (int nch = 1; nch <= 40 && nch <= D; ++nch) {
+    const int dc = (D + nch - 1) / nch;
+    const long long items = tiles * ((D + dc - 1) / dc);
+    const long long waves = (items + nsm - 1) / nsm;
+    const double cost = (double)waves * (dc + (kd == 3 ? 2.5 : 0.5));
+    if (cost < best_cost - 1e-9) { best_cost = cost; best_nch = nch; }
+  }
+  a.dchunk = (D + best_nch - 1) / best_nch; a.nchunks = (D + a.dchunk - 1) / a.dchunk;
+  a.nitems = (int)(tiles * a.nchunks);
+  const size_t slab = (size_t)(HTv + 2) * WT * (g0 + g1) * 2;
   int nslot = (int)((227 * 1024 - fixed) / slab);
   if (nslot > MAXSLOT) nslot = MAXSLOT;
   VXM_REQUIRE(nslot >= 4, "conv3d_tcs_fwd: not enough shared memory for the slab ring");
@@ -416,19 +442,28 @@ extern "C" int vxm_conv3d_tcs_fwd(const void* xa, const void* xb, const void* wp
   size_t smem = fixed + (size_t)nslot * slab;
   int grid = a.nitems < nsm ? a.nitems : nsm;
   cudaStream_t st = as_stream(stream);
-#define VXM_TCS_LAUNCH(KD_, G0_, G1_, CO_)                                                                                   \
-  do {                                                                                                                       \
-    VXM_CUDA(cudaFuncSetAttribute(conv_tcs_kernel<KD_, G0_, G1_, CO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    conv_tcs_kernel<KD_, G0_, G1_, CO_><<<grid, NTHREADS, smem, st>>>(a);                                                     \
+#define VXM_TCS_LAUNCH(KD_, G0_, G1_, CO_, HT_)                                                                                   \
+  do {                                                                                                                            \
+    VXM_CUDA(cudaFuncSetAttribute(conv_tcs_kernel<KD_, G0_, G1_, CO_, HT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    conv_tcs_kernel<KD_, G0_, G1_, CO_, HT_><<<grid, NTHREADS, smem, st>>>(a);                                                     \
+  } while (0)
+#define VXM_TCS_G8(KD_, CO_)                                                  \
+  do {                                                                        \
+    if (g0 == 16) VXM_TCS_LAUNCH(KD_, 16, 0, CO_, 8);                         \
+    else if (g0 == 32 && g1 == 0) VXM_TCS_LAUNCH(KD_, 32, 0, CO_, 8);         \
+    else VXM_TCS_LAUNCH(KD_, 32, 16, CO_, 8);                                 \
   } while (0)
 #define VXM_TCS_G(KD_, CO_)                                                   \
   do {                                                                        \
-    if (g0 == 16) VXM_TCS_LAUNCH(KD_, 16, 0, CO_);                            \
-    else if (g0 == 32 && g1 == 0) VXM_TCS_LAUNCH(KD_, 32, 0, CO_);            \
-    else if (g0 == 32) VXM_TCS_LAUNCH(KD_, 32, 16, CO_);                      \
-    else VXM_TCS_LAUNCH(KD_, 64, 0, CO_);                                     \
+    if (g0 == 16) VXM_TCS_LAUNCH(KD_, 16, 0, CO_, 4);                         \
+    else if (g0 == 32 && g1 == 0) VXM_TCS_LAUNCH(KD_, 32, 0, CO_, 4);         \
+    else if (g0 == 32) VXM_TCS_LAUNCH(KD_, 32, 16, CO_, 4);                   \
+    else VXM_TCS_LAUNCH(KD_, 64, 0, CO_, 4);                                  \
   } while (0)
-  if (kd == 3) { if (coutp == 16) VXM_TCS_G(3, 16); else if (coutp == 32) VXM_TCS_G(3, 32); else if (coutp == 48) VXM_TCS_G(3, 48); else VXM_TCS_G(3, 64); }
+  if (HTv == 8) {
+    if (kd == 3) { if (coutp == 16) VXM_TCS_G8(3, 16); else VXM_TCS_G8(3, 32); }
+    else { if (coutp == 16) VXM_TCS_G8(1, 16); else VXM_TCS_G8(1, 32); }
+  } else if (kd == 3) { if (coutp == 16) VXM_TCS_G(3, 16); else if (coutp == 32) VXM_TCS_G(3, 32); else if (coutp == 48) VXM_TCS_G(3, 48); else VXM_TCS_G(3, 64); }
   else { if (coutp == 16) VXM_TCS_G(1, 16); else if (coutp == 32) VXM_TCS_G(1, 32); else if (coutp == 48) VXM_TCS_G(1, 48); else VXM_TCS_G(1, 64); }
   return check_launch("conv3d_tcs_fwd");
 }
