@@ -17,7 +17,7 @@ using namespace vxm::tc;
 
 constexpr int WT = 32, WUSE = 30;      // tile: HT (4 or 8) rows x 32 columns (30 written), slab = (HT + 2) x 32 voxel rows
 constexpr int MAXSLOT = 8, MAXACC = 4;
-constexpr int NLOADER = 96, NTHREADS = 384;   // warps 0-3 epilogue group 0, 4 MMA issuer, 5-7 loader, 8-11 epilogue group 1
+constexpr int NLOADER = 96, NTHREADS = 512, NGRP = 3;   // warps 0-3 epilogue group 0, 4 MMA issuer, 5-7 loader, 8-11 / 12-15 epilogue groups 1 / 2
 
 struct ConvSArgs {
   const __nv_bfloat16* xa; const __nv_bfloat16* xb;
@@ -54,7 +54,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const ConvSArgs a
   constexpr int NC8 = (G0 + G1) / 8;                      // 16-byte chunks per voxel
   constexpr uint32_t SLAB0 = SROWS * W0, SLAB1 = SROWS * W1;
   constexpr int NN = 3 * COUT;   // MMA N: (kw, co)
-  constexpr int NACC = (4 * NN <= 512) ? 4 : 2;   // TMEM accumulators in flight (two epilogue groups alternate tiles)
+  // TMEM accumulators in flight = epilogue groups in use: group g owns accumulator g, so every mbarrier is waited on
+  // phase by phase (a group that skipped ahead on a barrier would alias its parity)
+  constexpr int NACC = (3 * NN <= 512) ? 3 : 2;
   extern __shared__ __align__(1024) uint8_t smem[];
   const bool halfk = (a.Ca + a.Cb == 8);                  // 8 real channels in a 16-channel group: chunk 1 is zero-filled
   constexpr uint32_t slab_bytes = SLAB0 + SLAB1;
@@ -222,12 +224,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const ConvSArgs a
       }
     }
   } else {
-    // ================================ EPILOGUE (2 groups x 4 warps; warp = tile row hh, lane = w') ==================
-    // Group g drains the tiles with (tile counter & 1) == g, so two tiles are in flight and the global-memory
-    // latencies of one (mask prefetch, stores) hide behind the other.
-    const int grp = warp >= 8 ? 1 : 0;
+    // ================================ EPILOGUE (3 groups x 4 warps; warp = tile row hh, lane = w') ==================
+    // Group g drains the accumulators with (accumulator counter % 3) == g: the per-tile epilogue is a ~1300-cycle
+    // dependent chain (TMEM load, 32 shuffles, bias / activation / mask, pack, store), so three tiles are kept in
+    // flight; with two groups the epilogue, not the tensor pipe, bounds the thin layers (profiles/r1_*).
+    const int grp = warp >= 12 ? 2 : (warp >= 8 ? 1 : 0);
+    uint32_t turn = 0, tphase = 0;   // accumulator counter % NACC; phase of this group's tfull barrier
     const int wq = warp & 3;
-    uint32_t acc_cnt = 0;
     const size_t HWp = (size_t)a.H * a.W;
     constexpr int NBR = COUT <= 32 ? COUT : 1;     // bias kept in registers for the (forward) layer widths
     float biasr[NBR];
@@ -241,10 +244,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const ConvSArgs a
       for (int d = d0; d < d1; ++d) {
 #pragma unroll
         for (int hb = 0; hb < NH; ++hb) {
-        if ((int)(acc_cnt & 1) != grp) { ++acc_cnt; continue; }
+        {
+          const bool mine = (int)turn == grp;
+          if (++turn == (uint32_t)NACC) turn = 0;
+          if (!mine) continue;
+        }
         const int h = ht * HT + hb * 4 + wq;
         const bool valid = lane >= 1 && lane <= WUSE && h < a.H && w < a.W;
-        const uint32_t acc = acc_cnt % NACC;
+        const uint32_t acc = (uint32_t)grp;
         const size_t vox = (((size_t)b * a.D + d) * a.H + h) * a.W + w;
         // prefetch the LeakyReLU-derivative mask of this voxel before waiting for the tensor core
         uint4 mreg[COUT / 8];
@@ -253,7 +260,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const ConvSArgs a
           for (int q = 0; q < COUT / 8; ++q)
             if (q * 8 < a.Cout) mreg[q] = __ldg(reinterpret_cast<const uint4*>(a.mask + vox * a.Cout) + q);
         }
-        mbar_wait(&tfull[acc], (acc_cnt / NACC) & 1);
+        mbar_wait(&tfull[acc], tphase);
+        tphase ^= 1;
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * (uint32_t)NN;
         const int c1 = a.out2 ? a.csplit : a.Cout;          // channels [0,c1) -> out, [c1,Cout) -> out2
@@ -313,7 +321,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const ConvSArgs a
             }
           }
         }
-        ++acc_cnt;
         }
       }
     }
