@@ -21,7 +21,11 @@ namespace vxm {
 
 constexpr int NTH = 16, NTW = 32, NHALO = 4;        // tile and max halo (window <= 9)
 constexpr int NIH = NTH + 2 * NHALO, NIW = NTW + 2 * NHALO;
-constexpr int NCC_ZCHUNK = 20;
+static int ncc_zchunk() {   // depth chunk per CTA (halo of wd - 1 slices is re-read per chunk); VXM_B200_NCC_ZCHUNK overrides
+  const char* e = getenv("VXM_B200_NCC_ZCHUNK");
+  int z = e ? atoi(e) : 20;
+  return z < 4 ? 4 : z;
+}
 
 struct NccArgs {
   const float* I;
@@ -31,7 +35,7 @@ struct NccArgs {
   float* out;              // fwd: loss scalar ; bwd: grad_J
   const float* grad_loss;  // bwd
   ReduceWork rw;
-  int B, D, H, W, wd, wh, ww;
+  int B, D, H, W, wd, wh, ww, zchunk;
   float nwin;              // prod(win)
   double scale;            // -1 / (B*D*H*W)
 };
@@ -47,9 +51,9 @@ __global__ void __launch_bounds__(256) ncc_kernel(NccArgs a) {
   const int tid = threadIdx.x;
   const int tx = tid & 31, ty = tid >> 5;  // ty in 0..7 -> rows ty and ty+8
   const int w0 = blockIdx.x * NTW, h0 = blockIdx.y * NTH;
-  const int nchunks = (a.D + NCC_ZCHUNK - 1) / NCC_ZCHUNK;
+  const int nchunks = (a.D + a.zchunk - 1) / a.zchunk;
   const int chunk = blockIdx.z % nchunks, b = blockIdx.z / nchunks;
-  const int z0 = chunk * NCC_ZCHUNK, z1 = min(z0 + NCC_ZCHUNK, a.D);
+  const int z0 = chunk * a.zchunk, z1 = min(z0 + a.zchunk, a.D);
   const int pd = WD / 2, ph = a.wh / 2, pw = a.ww / 2;
   const size_t HW = (size_t)a.H * a.W, DHW = HW * a.D;
   const float* f0 = (MODE == 0 ? a.I : a.saved_in) + (size_t)b * (MODE == 0 ? 1 : 3) * DHW;
@@ -220,7 +224,7 @@ static int ncc_check(int B, int D, int H, int W, int wd, int wh, int ww, dim3* g
     set_error("ncc: window (%d,%d,%d) unsupported (odd sizes 1..9 only)", wd, wh, ww);
     return VXM_ERR_UNSUPPORTED;
   }
-  int nchunks = (D + NCC_ZCHUNK - 1) / NCC_ZCHUNK;
+  int nchunks = (D + ncc_zchunk() - 1) / ncc_zchunk();
   *grid = dim3((W + NTW - 1) / NTW, (H + NTH - 1) / NTH, nchunks * B);
   VXM_REQUIRE((size_t)grid->x * grid->y * grid->z <= (size_t)kMaxReduceBlocks && grid->z <= 65535u,
               "ncc: volume too large for the reduction workspace");
@@ -252,7 +256,7 @@ extern "C" int vxm_ncc_fwd(const float* I, const float* J, float* loss, float* s
   NccArgs a{};
   a.I = I; a.J = J; a.saved_out = saved; a.out = loss; a.rw = as_reduce_work(work);
   a.B = B; a.D = D; a.H = H; a.W = W; a.wd = wd; a.wh = wh; a.ww = ww;
-  a.nwin = (float)(wd * wh * ww);
+  a.nwin = (float)(wd * wh * ww); a.zchunk = ncc_zchunk();
   a.scale = -1.0 / ((double)B * D * H * W);
   return ncc_launch<0>(a, grid, as_stream(stream));
 }
@@ -266,7 +270,7 @@ extern "C" int vxm_ncc_bwd(const float* I, const float* J, const float* saved, c
   NccArgs a{};
   a.I = I; a.J = J; a.saved_in = saved; a.out = grad_J; a.grad_loss = grad_loss;
   a.B = B; a.D = D; a.H = H; a.W = W; a.wd = wd; a.wh = wh; a.ww = ww;
-  a.nwin = (float)(wd * wh * ww);
+  a.nwin = (float)(wd * wh * ww); a.zchunk = ncc_zchunk();
   a.scale = -1.0 / ((double)B * D * H * W);
   return ncc_launch<1>(a, grid, as_stream(stream));
 }
