@@ -21,10 +21,22 @@ namespace vxm {
 
 constexpr int NTH = 16, NTW = 32, NHALO = 4;        // tile and max halo (window <= 9)
 constexpr int NIH = NTH + 2 * NHALO, NIW = NTW + 2 * NHALO;
-static int ncc_zchunk() {   // depth chunk per CTA (halo of wd - 1 slices is re-read per chunk); VXM_B200_NCC_ZCHUNK overrides
+// Depth chunk per CTA.  Every chunk re-reads wd - 1 halo slices, and the grid should fill the 2-CTA-per-SM slots in
+// whole waves: pick the chunk count that minimises waves x (slices per chunk + halo).  VXM_B200_NCC_ZCHUNK overrides.
+static int ncc_zchunk(int D, long long tiles, int wd) {
   const char* e = getenv("VXM_B200_NCC_ZCHUNK");
-  int z = e ? atoi(e) : 20;
-  return z < 4 ? 4 : z;
+  if (e && atoi(e) >= 4) return atoi(e);
+  const long long slots = 2LL * sm_count();
+  int best = D;
+  double best_cost = 1e300;
+  for (int nch = 1; nch <= D; ++nch) {
+    const int zc = (D + nch - 1) / nch;
+    if (zc < 8 && nch > 1) break;
+    const long long ctas = tiles * ((D + zc - 1) / zc);
+    const double cost = (double)((ctas + slots - 1) / slots) * (zc + wd - 1);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = zc; }
+  }
+  return best;
 }
 
 struct NccArgs {
@@ -41,7 +53,7 @@ struct NccArgs {
 };
 
 template <int MODE, int WD>
-__global__ void __launch_bounds__(256) ncc_kernel(NccArgs a) {
+__global__ void __launch_bounds__(256, 2) ncc_kernel(NccArgs a) {   // 2 CTAs per SM: the per-slice barriers of one overlap the loads of the other
   constexpr int NF = MODE == 0 ? 2 : 3;
   constexpr int NS = MODE == 0 ? 5 : 3;
   __shared__ __align__(16) float s_in[NF][NIH][NIW];
@@ -217,14 +229,16 @@ static int ncc_launch(const NccArgs& a, dim3 grid, cudaStream_t st) {
   return check_launch(MODE == 0 ? "ncc_fwd" : "ncc_bwd");
 }
 
-static int ncc_check(int B, int D, int H, int W, int wd, int wh, int ww, dim3* grid) {
+static int ncc_check(int B, int D, int H, int W, int wd, int wh, int ww, dim3* grid, int* zchunk) {
   VXM_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "ncc: non-positive dimension");
   auto okw = [](int w) { return w >= 1 && w <= 9 && (w & 1); };
   if (!(okw(wd) && okw(wh) && okw(ww))) {
     set_error("ncc: window (%d,%d,%d) unsupported (odd sizes 1..9 only)", wd, wh, ww);
     return VXM_ERR_UNSUPPORTED;
   }
-  int nchunks = (D + ncc_zchunk() - 1) / ncc_zchunk();
+  const int zc = ncc_zchunk(D, (long long)B * ((W + NTW - 1) / NTW) * ((H + NTH - 1) / NTH), wd);
+  *zchunk = zc;
+  int nchunks = (D + zc - 1) / zc;
   *grid = dim3((W + NTW - 1) / NTW, (H + NTH - 1) / NTH, nchunks * B);
   VXM_REQUIRE((size_t)grid->x * grid->y * grid->z <= (size_t)kMaxReduceBlocks && grid->z <= 65535u,
               "ncc: volume too large for the reduction workspace");
@@ -250,13 +264,14 @@ ReduceWork as_reduce_work(void* work) {
 extern "C" int vxm_ncc_fwd(const float* I, const float* J, float* loss, float* saved, void* work, int B,
                            int D, int H, int W, int wd, int wh, int ww, void* stream) {
   dim3 grid;
-  int rc = ncc_check(B, D, H, W, wd, wh, ww, &grid);
+  int zchunk = 0;
+  int rc = ncc_check(B, D, H, W, wd, wh, ww, &grid, &zchunk);
   if (rc) return rc;
   VXM_REQUIRE(I && J && loss && work, "ncc_fwd: null pointer");
   NccArgs a{};
   a.I = I; a.J = J; a.saved_out = saved; a.out = loss; a.rw = as_reduce_work(work);
   a.B = B; a.D = D; a.H = H; a.W = W; a.wd = wd; a.wh = wh; a.ww = ww;
-  a.nwin = (float)(wd * wh * ww); a.zchunk = ncc_zchunk();
+  a.nwin = (float)(wd * wh * ww); a.zchunk = zchunk;
   a.scale = -1.0 / ((double)B * D * H * W);
   return ncc_launch<0>(a, grid, as_stream(stream));
 }
@@ -264,13 +279,14 @@ extern "C" int vxm_ncc_fwd(const float* I, const float* J, float* loss, float* s
 extern "C" int vxm_ncc_bwd(const float* I, const float* J, const float* saved, const float* grad_loss,
                            float* grad_J, int B, int D, int H, int W, int wd, int wh, int ww, void* stream) {
   dim3 grid;
-  int rc = ncc_check(B, D, H, W, wd, wh, ww, &grid);
+  int zchunk = 0;
+  int rc = ncc_check(B, D, H, W, wd, wh, ww, &grid, &zchunk);
   if (rc) return rc;
   VXM_REQUIRE(I && J && saved && grad_loss && grad_J, "ncc_bwd: null pointer");
   NccArgs a{};
   a.I = I; a.J = J; a.saved_in = saved; a.out = grad_J; a.grad_loss = grad_loss;
   a.B = B; a.D = D; a.H = H; a.W = W; a.wd = wd; a.wh = wh; a.ww = ww;
-  a.nwin = (float)(wd * wh * ww); a.zchunk = ncc_zchunk();
+  a.nwin = (float)(wd * wh * ww); a.zchunk = zchunk;
   a.scale = -1.0 / ((double)B * D * H * W);
   return ncc_launch<1>(a, grid, as_stream(stream));
 }

@@ -100,16 +100,18 @@ struct AdjList {
   float w[ADJ_MAX];
 };
 
+constexpr int ADJ_ZPB = 8;   // input slices per block: the x / y tables are built once and reused
 __global__ void __launch_bounds__(256) resize_bwd_table_kernel(const float* __restrict__ gout, float* __restrict__ gx, ResizeGeom g) {
-  __shared__ AdjList lx[32], ly[8], lz[1];
+  __shared__ AdjList lx[32], ly[8], lz[ADJ_ZPB];
   const int tid = threadIdx.y * 32 + threadIdx.x;
   const int ix = blockIdx.x * 32 + threadIdx.x;
   const int iy = blockIdx.y * 8 + threadIdx.y;
-  const int iz = blockIdx.z % g.mz.in, bc = blockIdx.z / g.mz.in;
-  if (tid < 41) {
+  const int nzb = (g.mz.in + ADJ_ZPB - 1) / ADJ_ZPB;
+  const int iz0 = (blockIdx.z % nzb) * ADJ_ZPB, bc = blockIdx.z / nzb;
+  if (tid < 40 + ADJ_ZPB) {
     const AxisMap& m = tid < 32 ? g.mx : (tid < 40 ? g.my : g.mz);
-    const int i = tid < 32 ? blockIdx.x * 32 + tid : (tid < 40 ? blockIdx.y * 8 + (tid - 32) : iz);
-    AdjList& L = tid < 32 ? lx[tid] : (tid < 40 ? ly[tid - 32] : lz[0]);
+    const int i = tid < 32 ? blockIdx.x * 32 + tid : (tid < 40 ? blockIdx.y * 8 + (tid - 32) : iz0 + (tid - 40));
+    AdjList& L = tid < 32 ? lx[tid] : (tid < 40 ? ly[tid - 32] : lz[tid - 40]);
     L.n = 0;
     if (i < m.in) {
       int lo, hi;
@@ -124,18 +126,20 @@ __global__ void __launch_bounds__(256) resize_bwd_table_kernel(const float* __re
   if (ix >= g.mx.in || iy >= g.my.in) return;
   const AdjList& X = lx[threadIdx.x];
   const AdjList& Y = ly[threadIdx.y];
-  const AdjList& Z = lz[0];
   const float* gb = gout + (size_t)bc * g.mz.out * g.my.out * g.mx.out;
-  float acc = 0.f;
-  for (int a = 0; a < Z.n; ++a) {
-    for (int b = 0; b < Y.n; ++b) {
-      const float* r = gb + ((size_t)Z.o[a] * g.my.out + Y.o[b]) * g.mx.out;
-      float racc = 0.f;
-      for (int c = 0; c < X.n; ++c) racc += X.w[c] * __ldg(r + X.o[c]);
-      acc += Z.w[a] * Y.w[b] * racc;
+  for (int zz = 0; zz < ADJ_ZPB && iz0 + zz < g.mz.in; ++zz) {
+    const AdjList& Z = lz[zz];
+    float acc = 0.f;
+    for (int a = 0; a < Z.n; ++a) {
+      for (int b = 0; b < Y.n; ++b) {
+        const float* r = gb + ((size_t)Z.o[a] * g.my.out + Y.o[b]) * g.mx.out;
+        float racc = 0.f;
+        for (int c = 0; c < X.n; ++c) racc += X.w[c] * __ldg(r + X.o[c]);
+        acc += Z.w[a] * Y.w[b] * racc;
+      }
     }
+    gx[(((size_t)bc * g.mz.in + iz0 + zz) * g.my.in + iy) * g.mx.in + ix] = acc * (g.pre * g.post);
   }
-  gx[(((size_t)bc * g.mz.in + iz) * g.my.in + iy) * g.mx.in + ix] = acc * (g.pre * g.post);
 }
 
 __global__ void __launch_bounds__(256) resize_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gx, ResizeGeom g) {
@@ -196,7 +200,10 @@ extern "C" int vxm_resize_bwd(const float* grad_out, float* grad_x, int B, int C
   ResizeGeom g{make_map(Di, Do), make_map(Hi, Ho), make_map(Wi, Wo), B * C, pre, post};
   dim3 block(32, 8, 1), grid((Wi + 31) / 32, (Hi + 7) / 8, Di * B * C);
   auto fits = [](const AxisMap& m) { return m.in == m.out || (m.ratio > 0.f && 2.0f / m.ratio + 5.0f <= (float)ADJ_MAX + 2.f); };
-  if (fits(g.mz) && fits(g.my) && fits(g.mx)) resize_bwd_table_kernel<<<grid, block, 0, as_stream(stream)>>>(grad_out, grad_x, g);
+  if (fits(g.mz) && fits(g.my) && fits(g.mx)) {
+    dim3 gridt((Wi + 31) / 32, (Hi + 7) / 8, ((Di + ADJ_ZPB - 1) / ADJ_ZPB) * B * C);
+    resize_bwd_table_kernel<<<gridt, block, 0, as_stream(stream)>>>(grad_out, grad_x, g);
+  }
   else resize_bwd_kernel<<<grid, block, 0, as_stream(stream)>>>(grad_out, grad_x, g);
   return check_launch("resize_bwd");
 }
