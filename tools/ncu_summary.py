@@ -33,6 +33,15 @@ def main():
         rows = ncu_csv(rep, "raw")
         hdr, units = rows[0], rows[1]
         print("## `%s`\n" % rep.split("/")[-1])
+        # the source page holds one table per profiled launch, each introduced by a "Kernel Name" row
+        sections, cur = [], None
+        for x in ncu_csv(rep, "source"):
+            if x and x[0] == "Kernel Name":
+                cur = [x]
+                sections.append(cur)
+            elif cur is not None:
+                cur.append(x)
+        kidx = 0
         for r in rows[2:]:
             name = r[hdr.index("Kernel Name")]
             print("### `%s`\n" % name[:110])
@@ -46,11 +55,21 @@ def main():
                         pass
                     print("| %s (`%s`) | %s %s |" % (label, k, v, units[hdr.index(k)]))
             print()
-            src = ncu_csv(rep, "source", ["--kernel-name", "regex:" + name.split("<")[0].split("::")[-1].split("(")[0]])
+            # match the source table of this launch by kernel name (template arguments included)
+            import re
+            def fn(n):
+                m = re.search(r"(\w+<[^>]*>|\w+)\(", n.replace("(int)", "").replace(" ", ""))
+                return m.group(1) if m else n
+            key = fn(name)
+            src = []
+            for si, sec in enumerate(sections):
+                if sec is not None and len(sec[0]) > 1 and fn(sec[0][1]) == key:
+                    src, sections[si] = sec, None
+                    break
             if len(src) < 3:
                 continue
             h2 = src[1]
-            data = [x for x in src[2:] if len(x) == len(h2)]
+            data = [x for x in src[2:] if len(x) == len(h2) and x[h2.index('# Samples')].isdigit()]
             iS, iSrc = h2.index("# Samples"), h2.index("Source")
             stall = [i for i, h in enumerate(h2) if h.startswith("stall_") and "Not Issued" not in h]
             tot = sum(int(x[iS]) for x in data) or 1
