@@ -37,7 +37,6 @@ struct Wgrad2Args {
   float* bias_partial;                       // [grid][GOUT] or null
   int B, D, H, W;
   int tiles_h, tiles_w, dchunk, nchunks, nitems, nslot;
-  int boff_mode;
 };
 
 __host__ __device__ inline uint32_t swz(uint32_t off, uint32_t width) { return off ^ (((off >> 7) & (width / 16 - 1)) << 4); }
@@ -196,7 +195,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad2_kernel(const Wgrad2Args a)
           const uint32_t a_start = x_u32 + hslot * XSLAB;
           const uint32_t b_start = g_u32 + gs * GSLAB + (uint32_t)(GPAD - 1) * WG;
           const uint64_t adesc0 = make_desc_mn_swz<WA>(a_start, KD == 3 ? XSLAB : 0u, 0u);
-          const uint64_t bdesc0 = make_desc_mn_swz<WG>(b_start, (uint32_t)WG, a.boff_mode ? (b_start >> 7) : 0u);
+          const uint64_t bdesc0 = make_desc_mn_swz<WG>(b_start, (uint32_t)WG, 0u);   // base offset 0: the swizzle is a function of the absolute address (verified on B200: the matrix-base-offset form gives wrong sums)
           if (elect_one()) {
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh) {
@@ -344,24 +343,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad2_kernel(const Wgrad2Args a)
   }
 }
 
-// gw[co][ci_off + ci][tap] (+)= sum_cta partial[cta][tap][ci][co]   (fixed order -> deterministic); threads follow the
-// partial layout (co fastest) so the ncta reads per element coalesce.
-__global__ void wgrad2_reduce_kernel(const float* __restrict__ partial, float* __restrict__ gw, int ncta, int T, int G, int GOUT, int Cout,
-                                     int Cin_total, int ci_off, int ci_cnt, const float* __restrict__ bias_partial, float* __restrict__ gb,
-                                     int accumulate) {
+// gw[co][ci_off + ci][tap] (+)= sum_cta partial[cta][tap][ci][co]   (fixed order -> deterministic).  Block = 64 elements
+// x 4 quarters of the CTA range: threads follow the partial layout (co fastest) so the reads coalesce, and the four
+// quarter sums (combined in fixed order through shared memory) keep 4x more loads in flight than one serial loop.
+__global__ void __launch_bounds__(256) wgrad2_reduce_kernel(const float* __restrict__ partial, float* __restrict__ gw, int ncta, int T, int G,
+                                                            int GOUT, int Cout, int Cin_total, int ci_off, int ci_cnt,
+                                                            const float* __restrict__ bias_partial, float* __restrict__ gb, int accumulate) {
+  __shared__ float sh[4][64];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
   if (gb && blockIdx.x == 0 && threadIdx.x < Cout) {
     float acc = accumulate ? gb[threadIdx.x] : 0.f;
     for (int c = 0; c < ncta; ++c) acc += bias_partial[(size_t)c * GOUT + threadIdx.x];
     gb[threadIdx.x] = acc;
   }
   const int per_cta = T * G * GOUT;
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < per_cta; j += gridDim.x * blockDim.x) {
+  const int j = blockIdx.x * 64 + tx;
+  const int q = (ncta + 3) / 4, c0 = ty * q, c1 = min(c0 + q, ncta);
+  float acc = 0.f;
+  if (j < per_cta)
+    for (int c = c0; c < c1; ++c) acc += partial[(size_t)c * per_cta + j];
+  sh[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && j < per_cta) {
     const int co = j % GOUT, ci = (j / GOUT) % G, tap = j / (GOUT * G);
-    if (co >= Cout || ci >= ci_cnt) continue;
-    float acc = 0.f;
-    for (int c = 0; c < ncta; ++c) acc += partial[(size_t)c * per_cta + j];
-    float* dst = gw + ((size_t)co * Cin_total + ci_off + ci) * T + tap;
-    *dst = (accumulate ? *dst : 0.f) + acc;
+    if (co < Cout && ci < ci_cnt) {
+      const float tot = ((sh[0][tx] + sh[1][tx]) + sh[2][tx]) + sh[3][tx];
+      float* dst = gw + ((size_t)co * Cin_total + ci_off + ci) * T + tap;
+      *dst = (accumulate ? *dst : 0.f) + tot;
+    }
   }
 }
 
@@ -390,8 +399,6 @@ int wgrad2_launch(const void* x, int Cx, int up, const void* gz, int Cg, float* 
   a.gz = (const __nv_bfloat16*)gz; a.Cg = Cg;
   a.B = B; a.D = D; a.H = H; a.W = W;
   a.tiles_h = (H + TH - 1) / TH; a.tiles_w = (W + TUSE - 1) / TUSE;
-  const char* bo = getenv("VXM_B200_WGRAD_BOFF");
-  a.boff_mode = bo ? atoi(bo) : 0;
   const int G = Cx <= 16 ? 16 : 32, GOUT = Cg <= 16 ? 16 : 32;
   const int nsm = sm_count();
   // depth chunking: balance the persistent CTAs (waves of nsm items) against the 2 halo slabs every chunk re-loads
@@ -432,7 +439,7 @@ int wgrad2_launch(const void* x, int Cx, int up, const void* gz, int Cg, float* 
   int rc = check_launch("conv3d_tc_wgrad2");
   if (rc) return rc;
   const int T = kd * 9, per_cta = T * G * GOUT;
-  wgrad2_reduce_kernel<<<(per_cta + 255) / 256, 256, 0, st>>>(a.partial, grad_w, grid, T, G, GOUT, Cout_real, Cin_total, ci_off, ci_cnt,
+  wgrad2_reduce_kernel<<<(per_cta + 63) / 64, 256, 0, st>>>(a.partial, grad_w, grid, T, G, GOUT, Cout_real, Cin_total, ci_off, ci_cnt,
                                                               a.bias_partial, grad_b, accumulate);
   return check_launch("conv3d_tc_wgrad2_reduce");
 }

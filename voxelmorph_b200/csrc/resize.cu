@@ -42,14 +42,15 @@ struct ResizeGeom {
   float pre, post;
 };
 
+constexpr int RS_ZPB = 4;
 __global__ void __launch_bounds__(256) resize_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, ResizeGeom g) {
   int ox = blockIdx.x * 32 + threadIdx.x;
   int oy = blockIdx.y * 8 + threadIdx.y;
-  int oz = blockIdx.z % g.mz.out, bc = blockIdx.z / g.mz.out;
+  const int nzb = (g.mz.out + RS_ZPB - 1) / RS_ZPB;     // RS_ZPB output slices per block share the x / y index arithmetic
+  const int oz0 = (blockIdx.z % nzb) * RS_ZPB, bc = blockIdx.z / nzb;
   if (ox >= g.mx.out || oy >= g.my.out) return;
-  int z0, z1, y0, y1, x0, x1;
-  float lz0, lz1, ly0, ly1, lx0, lx1;
-  src_index(g.mz, oz, z0, z1, lz0, lz1);
+  int y0, y1, x0, x1;
+  float ly0, ly1, lx0, lx1;
   src_index(g.my, oy, y0, y1, ly0, ly1);
   src_index(g.mx, ox, x0, x1, lx0, lx1);
   const float* xb = x + (size_t)bc * g.mz.in * g.my.in * g.mx.in;
@@ -59,15 +60,23 @@ __global__ void __launch_bounds__(256) resize_fwd_kernel(const float* __restrict
     const float* r = xb + z * sD + y * sH;
     return __fmul_rn(__ldg(r + x0), pre) * lx0 + __fmul_rn(__ldg(r + x1), pre) * lx1;
   };
-  float p0 = row(z0, y0) * ly0 + row(z0, y1) * ly1;
-  float v;
-  if (z1 != z0 || g.mz.in != g.mz.out) {
-    float p1 = row(z1, y0) * ly0 + row(z1, y1) * ly1;
-    v = p0 * lz0 + p1 * lz1;
-  } else {
-    v = p0;  // l0 = 1, l1 = 0
+#pragma unroll
+  for (int zz = 0; zz < RS_ZPB; ++zz) {
+    const int oz = oz0 + zz;
+    if (oz >= g.mz.out) break;
+    int z0, z1;
+    float lz0, lz1;
+    src_index(g.mz, oz, z0, z1, lz0, lz1);
+    float p0 = row(z0, y0) * ly0 + row(z0, y1) * ly1;
+    float v;
+    if (z1 != z0 || g.mz.in != g.mz.out) {
+      float p1 = row(z1, y0) * ly0 + row(z1, y1) * ly1;
+      v = p0 * lz0 + p1 * lz1;
+    } else {
+      v = p0;  // l0 = 1, l1 = 0
+    }
+    out[(((size_t)bc * g.mz.out + oz) * g.my.out + oy) * g.mx.out + ox] = v * g.post;
   }
-  out[(((size_t)bc * g.mz.out + oz) * g.my.out + oy) * g.mx.out + ox] = v * g.post;
 }
 
 // adjoint weight of output index o on input index i along one axis
@@ -187,7 +196,7 @@ extern "C" int vxm_resize_fwd(const float* x, float* out, int B, int C, int Di, 
   if (rc) return rc;
   VXM_REQUIRE(x && out, "resize_fwd: null pointer");
   ResizeGeom g{make_map(Di, Do), make_map(Hi, Ho), make_map(Wi, Wo), B * C, pre, post};
-  dim3 block(32, 8, 1), grid((Wo + 31) / 32, (Ho + 7) / 8, Do * B * C);
+  dim3 block(32, 8, 1), grid((Wo + 31) / 32, (Ho + 7) / 8, ((Do + RS_ZPB - 1) / RS_ZPB) * B * C);
   resize_fwd_kernel<<<grid, block, 0, as_stream(stream)>>>(x, out, g);
   return check_launch("resize_fwd");
 }
