@@ -382,8 +382,7 @@ def b200_arm(args):
         conv_total_ms = sum(x.elapsed_time(y) for x, y in conv_ms)
         n_conv_launches = len(conv_ms)
     if rank != 0:
-        if world > 1:
-            torch.distributed.destroy_process_group()
+        _leave(world, rank)
         return
     _, flops_step = conv_flops_per_step(shape)
     ach = flops_step / (conv_total_ms * 1e-3) / 1e12
@@ -423,8 +422,42 @@ def b200_arm(args):
                 clocks=clk, e2e=e2e, gpu_launches=int(launches), launches_per_step=launches / K,
                 roofline=roofline, kernels=kernels, cpu_baseline=cpu)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        torch.distributed.destroy_process_group()
+    _leave(world, rank)
+
+
+def _leave(world, rank=None):
+    """End of a rank's work.  Under torchrun every rank leaves with os._exit(0), rank 0 last: the captured CUDA graph
+    still holds NCCL kernels, and tearing the process group down with it alive (destroy_process_group / interpreter
+    shutdown) blocked both ranks after the JSON line had been printed (2 x B200, round 1).  The ranks meet on the
+    rendezvous store (no collective): rank 0 posts `bench_done`, the others acknowledge, then everybody exits."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world <= 1:
+        return
+    import datetime
+    import torch
+    import torch.distributed as dist
+    try:
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        store = dist.distributed_c10d._get_default_store()
+        store.set_timeout(datetime.timedelta(seconds=1800))
+        if rank is None:
+            rank = dist.get_rank()
+        if rank == 0:
+            store.set("bench_done", "1")
+            t0 = time.time()
+            while store.add("bench_ack", 0) < world - 1 and time.time() - t0 < 60.0:
+                time.sleep(0.05)
+        else:
+            store.wait(["bench_done"])      # rank 0 may still be timing its CPU baseline
+            store.add("bench_ack", 1)
+            time.sleep(0.2)
+    except Exception as e:  # noqa: BLE001 - leaving must not fail
+        print("bench.py: exit rendezvous skipped (%s)" % e, file=sys.stderr)
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def kernel_rooflines(vxm, dev, shape, peaks):
