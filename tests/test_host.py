@@ -148,3 +148,30 @@ def test_data_parallel_logic_gloo_world2(tmp_path):
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert (tmp_path / "ok_0").exists() and (tmp_path / "ok_1").exists()
+
+
+def test_bench_ranks_leave_together_under_torchrun(tmp_path):
+    """bench.py's end-of-run rendezvous (store + os._exit, no collective): rank 0 finishes last, every rank exits 0 and
+    nothing after `_leave` runs.  World size 3 on CPU with gloo."""
+    import socket
+    script = tmp_path / "leave.py"
+    script.write_text(
+        "import sys, time\n"
+        "sys.path.insert(0, %r)\n"
+        "import torch, torch.distributed as dist\n"
+        "import bench\n"
+        "dist.init_process_group('gloo')\n"
+        "r, w = dist.get_rank(), dist.get_world_size()\n"
+        "t = torch.ones(1); dist.all_reduce(t)\n"
+        "if r == 0:\n"
+        "    time.sleep(1.5)\n"
+        "    print('RESULT', float(t), flush=True)\n"
+        "bench._leave(w, r)\n"
+        "print('NOT REACHED', flush=True)\n" % ROOT)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "3", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=240)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert "RESULT 3.0" in p.stdout and "NOT REACHED" not in p.stdout
