@@ -13,6 +13,7 @@ from . import losses
 from . import modelio
 from . import optim
 from . import dist
+from . import generators
 from .networks import default_unet_features
 
-__all__ = ["layers", "networks", "losses", "modelio", "optim", "dist", "default_unet_features"]
+__all__ = ["layers", "networks", "losses", "modelio", "optim", "dist", "generators", "default_unet_features"]
