@@ -310,3 +310,56 @@ def adam_step(p, g, m, v, step, lr=1e-4, b1=0.9, b2=0.999, eps=1e-8):
     denom = np.sqrt(v) / np.sqrt(bc2) + eps
     p = p - (lr / bc1) * m / denom
     return p, m, v
+
+
+# --------------------------------------------------------------------------------------
+# Evaluation helpers of the "next" rows N2 / N3  (reference voxelmorph/py/utils.py:265-287, :473-516)
+# --------------------------------------------------------------------------------------
+
+def dice_overlap(a1, a2, labels=None, include_zero=False):
+    """Per-label Dice overlap of two label maps (py/utils.py:265-287, used by scripts/tf/test.py:76-121).
+
+    labels=None: every label present in either map, ascending; label 0 dropped unless include_zero.
+    2|A∩B| / max(|A| + |B|, eps) with eps = np.finfo(float).eps, float64."""
+    a1, a2 = np.asarray(a1), np.asarray(a2)
+    if labels is None:
+        labels = np.union1d(np.unique(a1), np.unique(a2))
+    labels = np.asarray(labels)
+    if not include_zero:
+        labels = labels[labels != 0]
+    out = np.zeros(len(labels), dtype=np.float64)
+    for i, lab in enumerate(labels):
+        m1, m2 = a1 == lab, a2 == lab
+        out[i] = 2.0 * np.count_nonzero(m1 & m2) / max(float(np.count_nonzero(m1) + np.count_nonzero(m2)), np.finfo(float).eps)
+    return out
+
+
+def _central_diff(x, axis):
+    """np.gradient along one axis with unit spacing: central differences inside, first-order one-sided at both ends."""
+    x = np.moveaxis(np.asarray(x, dtype=np.float64), axis, 0)
+    g = np.empty_like(x)
+    if x.shape[0] == 1:
+        raise ValueError("gradient needs at least 2 samples along every axis")
+    g[1:-1] = (x[2:] - x[:-2]) / 2.0
+    g[0] = x[1] - x[0]
+    g[-1] = x[-1] - x[-2]
+    return np.moveaxis(g, 0, axis)
+
+
+def jacobian_determinant(disp):
+    """det of the Jacobian of the map x -> x + disp(x) for a (*vol, nd) displacement field, nd in (2, 3)
+    (py/utils.py:473-516; the identity grid comes from pystrum.pynd.ndutils.volsize2ndgrid == np.meshgrid(indexing='ij');
+    spatial derivatives are np.gradient's).  Values <= 0 mark folds (scripts/torch/register.py:63-97 consumers)."""
+    disp = np.asarray(disp, dtype=np.float64)
+    vol = disp.shape[:-1]
+    nd = len(vol)
+    assert nd in (2, 3) and disp.shape[-1] == nd, "flow has to be 2D or 3D"
+    grid = np.stack(np.meshgrid(*[np.arange(s) for s in vol], indexing="ij"), axis=-1)
+    phi = disp + grid
+    d = [_central_diff(phi, ax) for ax in range(nd)]       # d[a][..., c] = d phi_c / d x_a
+    if nd == 2:
+        return d[0][..., 0] * d[1][..., 1] - d[1][..., 0] * d[0][..., 1]
+    dx, dy, dz = d
+    return (dx[..., 0] * (dy[..., 1] * dz[..., 2] - dy[..., 2] * dz[..., 1])
+            - dx[..., 1] * (dy[..., 0] * dz[..., 2] - dy[..., 2] * dz[..., 0])
+            + dx[..., 2] * (dy[..., 0] * dz[..., 1] - dy[..., 1] * dz[..., 0]))

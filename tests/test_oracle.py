@@ -153,3 +153,20 @@ def test_adam_restatement():
         opt.step()
         p, m, v = spec_np.adam_step(p, g, m, v, step, lr=1e-3)
         np.testing.assert_allclose(tp.detach().numpy(), p, rtol=1e-12, atol=1e-14)
+
+
+def test_eval_helpers_known_answers():
+    """Oracle of the next rows N2 / N3 (Dice overlap, Jacobian determinant): closed-form cases."""
+    from oracle import spec_np
+    for shape in ((6, 7), (5, 6, 7)):
+        nd = len(shape)
+        grid = np.stack(np.meshgrid(*[np.arange(s, dtype=np.float64) for s in shape], indexing="ij"), -1)
+        assert np.allclose(spec_np.jacobian_determinant(np.zeros(shape + (nd,))), 1.0)          # identity map
+        assert np.allclose(spec_np.jacobian_determinant(0.1 * grid), 1.1 ** nd)                 # uniform dilation
+        fold = -2.0 * grid                                                                       # x -> -x: orientation flips per axis
+        assert np.allclose(spec_np.jacobian_determinant(fold), (-1.0) ** nd)
+    a = np.array([[0, 1, 1], [2, 2, 0]])
+    assert np.array_equal(spec_np.dice_overlap(a, a), [1.0, 1.0])
+    b = np.array([[0, 1, 0], [2, 0, 0]])
+    assert np.allclose(spec_np.dice_overlap(a, b), [2 * 1 / 3, 2 * 1 / 3])
+    assert np.allclose(spec_np.dice_overlap(a, b, labels=[5]), [0.0])

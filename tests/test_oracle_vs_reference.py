@@ -53,3 +53,21 @@ def test_network_live(vxm_ref):
         a = m(t(s), t(g))
         b = ref_torch.vxm_forward(sd, m.config, t(s), t(g))
     assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+def test_eval_helpers_live(vxm_ref):
+    """Next rows N2 / N3: Dice overlap and Jacobian determinant restatements vs reference py/utils.py:265-287, :473-516
+    (pystrum's volsize2ndgrid, absent here and stubbed at import, is supplied as its documented np.meshgrid(indexing='ij'))."""
+    import sys
+    nd_mod = sys.modules["pystrum.pynd.ndutils"]
+    if not hasattr(nd_mod, "volsize2ndgrid"):
+        nd_mod.volsize2ndgrid = lambda volshape: np.meshgrid(*[np.arange(s) for s in volshape], indexing="ij")
+    utils = vxm_ref.py.utils
+    rng = np.random.RandomState(5)
+    a, b = rng.randint(0, 5, size=(9, 10, 11)), rng.randint(0, 6, size=(9, 10, 11))
+    assert np.array_equal(utils.dice(a, b), spec_np.dice_overlap(a, b))
+    assert np.array_equal(utils.dice(a, b, labels=[1, 3, 7], include_zero=True), spec_np.dice_overlap(a, b, [1, 3, 7], True))
+    for shape in ((7, 9), (6, 7, 8)):
+        disp = cases.smooth_field(11, len(shape), shape, scale=3.0)[0]        # (nd, *vol)
+        disp = np.moveaxis(disp, 0, -1).astype(np.float64)
+        np.testing.assert_allclose(spec_np.jacobian_determinant(disp), utils.jacobian_determinant(disp), rtol=0, atol=1e-12)
