@@ -26,8 +26,8 @@ UNIT = "vol-pairs/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--shape", type=int, nargs=3, default=list(FULL), help="debug only; the metric is quoted at 160 192 224")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -76,7 +76,7 @@ class Clocks:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._pump, daemon=True)
             self.th.start()
@@ -85,18 +85,30 @@ class Clocks:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples taken in [t0, t1] (host clock).  The sampler is started before the warm-up so that it is
+        already streaming; when the timed region is shorter than the sampling period the nearest sample taken under the
+        same load (warm-up steps run back to back with the timed ones) is used and `window` says so."""
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.06)   # let the sample that covers the end of the region arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
-        for r in self.rows:
+        rows, window = list(self.rows), "timed region"
+        if t0 is not None:
+            inside = [r for r in rows if t0 <= r[0] <= t1 + 0.06]
+            if inside:
+                rows = inside
+            elif rows:
+                rows = [min(rows, key=lambda r: abs(r[0] - 0.5 * (t0 + t1)))]
+                window = "nearest sample under load (timed region shorter than the 50 ms sampling period)"
+        for _, r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 8:
                 continue
@@ -110,7 +122,7 @@ class Clocks:
         if not sm:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
         return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), power_w_max=max(pw), samples=len(sm),
-                    reasons=sorted(reasons))
+                    reasons=sorted(reasons), window=window)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -263,26 +275,28 @@ def b200_arm(args):
 
     # ---- warm-up ---------------------------------------------------------------------------------
     W, K = max(3, args.warmup), args.steps
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
     for i in range(W):
         step(*pairs_dev[i % NPAIR])
     barrier()
 
     # ---- device-resident timed region ------------------------------------------------------------
-    clocks = Clocks(local)
-    if rank == 0:
-        clocks.start()
     n0 = vxm._lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_host0 = time.time()
     e0.record()
     for i in range(K):
         step(*pairs_dev[i % NPAIR])
     e1.record()
     barrier()
+    t_host1 = time.time()
     ms = e0.elapsed_time(e1)
     launches = (launches_per_step * K) if graphed else (vxm._lib.launch_count() - n0)
     ms = vdist.max_over_ranks(ms, dev)
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop(t_host0, t_host1) if rank == 0 else None
     value = world * K / (ms * 1e-3)
 
     # ---- end-to-end: host buffers, H2D of the pair + D2H of the loss inside the timed region --------
