@@ -14,6 +14,7 @@ from . import modelio
 from . import optim
 from . import dist
 from . import generators
+from . import utils
 from .networks import default_unet_features
 
-__all__ = ["layers", "networks", "losses", "modelio", "optim", "dist", "generators", "default_unet_features"]
+__all__ = ["layers", "networks", "losses", "modelio", "optim", "dist", "generators", "utils", "default_unet_features"]
