@@ -503,28 +503,47 @@ def kernel_rooflines(vxm, dev, shape, peaks):
         out[name] = dict(bound="hbm", achieved=gbs, peak=peaks["hbm"], unit="GB/s", frac=gbs / peaks["hbm"], us=t * 1e3,
                          algorithmic_bytes=nbytes, note=note)
 
+    src = torch.rand((1, 1) + shape, device=dev)
+    smooth = lambda shp, sig: (torch.nn.functional.interpolate(  # noqa: E731  registration-like smooth displacement field
+        torch.randn((1, 3) + tuple(max(2, s // 16) for s in shp), device=dev) * sig, size=shp, mode="trilinear",
+        align_corners=True).contiguous())
+    flow = smooth(shape, 3.0)
+    rough = torch.randn((1, 3) + shape, device=dev) * 3.0
+    st = vxm.layers.SpatialTransformer(shape)
+    stn = vxm.layers.SpatialTransformer(shape, mode="nearest")
+    vel = smooth(half, 2.0)
+    vi = vxm.layers.VecInt(half, 7)
+    down, up = vxm.layers.ResizeTransform(2, 3), vxm.layers.ResizeTransform(0.5, 3)
+    I, J = torch.rand((1, 1) + shape, device=dev), torch.rand((1, 1) + shape, device=dev)
+    ncc = vxm.losses.NCC().loss
     with torch.no_grad():
-        src = torch.rand((1, 1) + shape, device=dev)
-        smooth = lambda shp, sig: (torch.nn.functional.interpolate(  # noqa: E731  registration-like smooth displacement field
-            torch.randn((1, 3) + tuple(max(2, s // 16) for s in shp), device=dev) * sig, size=shp, mode="trilinear",
-            align_corners=True).contiguous())
-        flow = smooth(shape, 3.0)
-        rough = torch.randn((1, 3) + shape, device=dev) * 3.0
-        st = vxm.layers.SpatialTransformer(shape)
-        stn = vxm.layers.SpatialTransformer(shape, mode="nearest")
         timeit(lambda: st(src, flow), V * 20, "warp_fwd_linear", "C=1, smooth flow sigma=3 voxels (registration-like)")
-        timeit(lambda: stn(src, flow), V * 20, "warp_fwd_nearest", "C=1, smooth flow")
+        timeit(lambda: stn(src, flow), V * 20, "warp_fwd_nearest", "C=1, smooth flow; exact replay of the reference's coordinate arithmetic (bit-exact labels)")
         timeit(lambda: st(src, rough), V * 20, "warp_fwd_linear_white_noise_flow", "C=1, i.i.d. N(0,3^2) flow per voxel (worst-case gather locality)")
-        vel = smooth(half, 2.0)
-        vi = vxm.layers.VecInt(half, 7)
         timeit(lambda: vi(vel), Vh * 24 * 7, "vecint_fwd_7steps", "single cooperative launch; field is L2 resident, so frac can "
                "exceed 1 against the HBM peak")
-        down, up = vxm.layers.ResizeTransform(2, 3), vxm.layers.ResizeTransform(0.5, 3)
         timeit(lambda: down(flow), (V + Vh) * 12, "resize_down")
         timeit(lambda: up(vel), (V + Vh) * 12, "resize_up")
-        I, J = torch.rand((1, 1) + shape, device=dev), torch.rand((1, 1) + shape, device=dev)
-        ncc = vxm.losses.NCC().loss
-        timeit(lambda: ncc(I, J), V * 8, "ncc_fwd")
+        timeit(lambda: ncc(I, J), V * 8, "ncc_fwd", "no saved fields (inference / validation)")
+
+    # backward legs: the autograd node's backward is timed alone (forward outside the events); bytes per SURVEY 8(d)
+    def timeit_bwd(make, nbytes, name, note=""):
+        def run():
+            y, g = make()
+            return lambda: y.backward(g, retain_graph=True)
+        fn = run()
+        timeit(fn, nbytes, name, note)
+
+    fl = flow.clone().requires_grad_(True)
+    timeit_bwd(lambda: (st(src, fl), torch.ones((1, 1) + shape, device=dev)), V * 36, "warp_bwd_linear",
+               "d/d flow only (the moving image needs no gradient in training): reads grad, flow, src; writes 3 planes")
+    vl = vel.clone().requires_grad_(True)
+    timeit_bwd(lambda: (vi(vl), torch.ones_like(vel)), Vh * 36 * 7, "vecint_bwd_7steps", "single cooperative launch, red.global.add.v4 scatter")
+    timeit_bwd(lambda: (up(vl), torch.ones((1, 3) + shape, device=dev)), (V + Vh) * 12, "resize_up_bwd", "adjoint of the x2 upsampling (reads the full-resolution gradient)")
+    timeit_bwd(lambda: (down(fl), torch.ones((1, 3) + half, device=dev)), (V + Vh) * 12, "resize_down_bwd")
+    Jg = J.clone().requires_grad_(True)
+    timeit(lambda: ncc(I, Jg), V * 8 + V * 12, "ncc_fwd_training", "forward that also stores the 3 fields the backward box-filters")
+    timeit_bwd(lambda: (ncc(I, Jg), torch.ones((), device=dev)), V * 12 + V * 12, "ncc_bwd", "reads I, J + 3 saved fields, writes dJ")
     return out
 
 

@@ -42,6 +42,10 @@ extern "C" {
  * multiply by fl(1/(S-1)) (what torch's CUDA `tensor / python_scalar` computes). */
 #define VXM_ARITH_TRUE_DIV 0
 #define VXM_ARITH_RECIPROCAL 1
+/* linear mode only: coord = (p + flow) * (Ssrc-1)/(S-1) without replaying the reference's fp32 round trip; results
+ * agree with the exact modes to a few 1e-6 of the value range (north_star tolerance for floating point: 1e-4) and the
+ * kernels are memory bound instead of instruction bound.  The nearest mode always replays the exact arithmetic. */
+#define VXM_ARITH_FAST 2
 
 const char* vxm_last_error(void);
 /* library / build identification ("vxm_b200 <version> sm_100a") */
@@ -75,6 +79,11 @@ int vxm_vecint_fwd(const float* vel, float* out, float* states, void* work,
  * 2 * B*nd*D*H*W floats of scratch. */
 int vxm_vecint_bwd(const float* grad_out, const float* states, float* grad_vel, void* work,
                    int B, int D, int H, int W, int nd, int nsteps, int arith, void* stream);
+/* arith == VXM_ARITH_FAST (3-D, nsteps >= 1): the launch keeps the field in an interleaved float4 (z,y,x,0) layout.
+ * `states` then holds vxm_vecint_fast_states_bytes() bytes (nsteps float4 fields), `work`
+ * vxm_vecint_fast_work_bytes(backward) bytes (2 float4 fields forward without states, 3 backward). */
+size_t vxm_vecint_fast_states_bytes(int B, int D, int H, int W, int nsteps);
+size_t vxm_vecint_fast_work_bytes(int B, int D, int H, int W, int backward);
 
 /* ---- ResizeTransform: reference voxelmorph/torch/layers.py:85-97 (F.interpolate :88,:94) ----
  * out = post * lerp(pre * x) with align_corners=True linear interpolation.
@@ -172,6 +181,11 @@ size_t vxm_conv3d_tcs_packed_bytes(int cin_eff, int coutp, int kd);
 int vxm_conv3d_tcs_pack(const float* w, void* wpk, int Cout, int Cin, int kd, int coutp, int transposed, void* stream);
 int vxm_conv3d_tcs_supported(int Ca, int Cb, int Cout);
 int vxm_conv3d_tcs_fwd(const void* xa, const void* xb, const void* wpk, const float* bias, void* out, const void* mask,
+                       int B, int D, int H, int W, int Ca, int Cb, int up, int Cout, int coutp, int kd, int out_mode,
+                       float slope, void* out2, int csplit, void* stream);
+/* variant of the above with two alternating MMA-issuing warps (8-row tiles only: Ca + Cb in {8,16,32,48}, padded
+ * Cout in {16,32}); same arguments, weights packed by vxm_conv3d_tcs_pack.  Selected with VXM_B200_TCS2=1. */
+int vxm_conv3d_tcs2_fwd(const void* xa, const void* xb, const void* wpk, const float* bias, void* out, const void* mask,
                        int B, int D, int H, int W, int Ca, int Cb, int up, int Cout, int coutp, int kd, int out_mode,
                        float slope, void* out2, int csplit, void* stream);
 /* Weight (and bias) gradient on tensor cores.  x sources as in vxm_conv3d_tc_fwd (the layer's forward input);

@@ -27,6 +27,8 @@ SIGNATURES = {
     "vxm_vecint_workspace_bytes": (c_sz, [c_i] * 6),
     "vxm_vecint_fwd": (c_i, [c_f, c_f, c_f, c_f] + [c_i] * 7 + [c_f]),
     "vxm_vecint_bwd": (c_i, [c_f, c_f, c_f, c_f] + [c_i] * 7 + [c_f]),
+    "vxm_vecint_fast_states_bytes": (c_sz, [c_i] * 5),
+    "vxm_vecint_fast_work_bytes": (c_sz, [c_i] * 5),
     "vxm_resize_fwd": (c_i, [c_f, c_f] + [c_i] * 8 + [c_fl, c_fl, c_f]),
     "vxm_resize_bwd": (c_i, [c_f, c_f] + [c_i] * 8 + [c_fl, c_fl, c_f]),
     "vxm_ncc_workspace_bytes": (c_sz, [c_i] * 4),
@@ -54,6 +56,7 @@ SIGNATURES = {
     "vxm_conv3d_tcs_pack": (c_i, [c_f, c_f] + [c_i] * 5 + [c_f]),
     "vxm_conv3d_tcs_supported": (c_i, [c_i] * 3),
     "vxm_conv3d_tcs_fwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f] + [c_i] * 11 + [c_fl, c_f, c_i, c_f]),
+    "vxm_conv3d_tcs2_fwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f] + [c_i] * 11 + [c_fl, c_f, c_i, c_f]),
     "vxm_conv3d_tc_wgrad_workspace_bytes": (c_sz, [c_i]),
     "vxm_conv3d_tc_wgrad": (c_i, [c_f, c_f, c_f, c_f, c_i, c_f, c_f, c_f, c_i, c_f, c_f, c_f] + [c_i] * 12 + [c_f]),
     "vxm_pool2_ndhwc_bf16": (c_i, [c_f, c_f] + [c_i] * 6 + [c_f]),

@@ -2,9 +2,18 @@
 // resampling of a flow field fused with its rescaling,  out = post * lerp(pre * x).
 //
 // Index / weight arithmetic follows ATen UpSample.h:271-296 (area_pixel_compute_scale /
-// _source_index) and :442-475 (guard_index_and_lambda); the lerp is evaluated innermost axis
-// first like ATen's generic N-d kernel.  The backward is a deterministic gather-form adjoint
-// (the reference's autograd reaches ATen's atomicAdd-based upsample_trilinear3d_backward).
+// _source_index) and :442-475 (guard_index_and_lambda).  The backward is a deterministic gather-form
+// adjoint (the reference's autograd reaches ATen's atomicAdd-based upsample_trilinear3d_backward).
+//
+// Both directions are "column marching" kernels: a thread owns one (x, y) position, walks a chunk of z
+// and carries every channel of the field (the index / weight arithmetic of x and y is done once per thread,
+// of z once per slice, and is shared by the channels):
+//   forward  — the x/y-interpolated values of the two source planes a slice needs stay in registers; when
+//              upsampling, consecutive output slices share a source plane, so a new slice costs ~one plane
+//              (4 loads per channel) instead of two;
+//   backward — the thread walks the OUTPUT-gradient planes that touch its z chunk, reduces each over its
+//              short x / y adjoint lists (register resident, contiguous ranges) and adds the result to the
+//              (at most two) input slices the plane interpolates from, held in two running accumulators.
 //
 // Algorithmic bytes (fp32): 4*C*(V_in + V_out) forward, the same backward.
 #include "common.cuh"
@@ -38,44 +47,67 @@ __device__ __forceinline__ void src_index(const AxisMap& m, int o, int& i0, int&
 
 struct ResizeGeom {
   AxisMap mz, my, mx;
-  int BC;
-  float pre, post;
+  int BC, zchunk, nzc;
+  float scale;   // pre * post
 };
 
-constexpr int RS_ZPB = 4;
+constexpr int RS_ZCHUNK = 16;
+
+// x/y-interpolated value of one source plane for NC channels
+template <int NC>
+__device__ __forceinline__ void plane_xy(const float* __restrict__ p, size_t cstride, int o00, int o01, int o10, int o11,
+                                         float lx0, float lx1, float ly0, float ly1, float (&v)[NC]) {
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const float* q = p + (size_t)c * cstride;
+    const float r0 = __ldg(q + o00) * lx0 + __ldg(q + o01) * lx1;
+    const float r1 = __ldg(q + o10) * lx0 + __ldg(q + o11) * lx1;
+    v[c] = r0 * ly0 + r1 * ly1;
+  }
+}
+
+template <int NC>
 __global__ void __launch_bounds__(256) resize_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, ResizeGeom g) {
-  int ox = blockIdx.x * 32 + threadIdx.x;
-  int oy = blockIdx.y * 8 + threadIdx.y;
-  const int nzb = (g.mz.out + RS_ZPB - 1) / RS_ZPB;     // RS_ZPB output slices per block share the x / y index arithmetic
-  const int oz0 = (blockIdx.z % nzb) * RS_ZPB, bc = blockIdx.z / nzb;
+  const int ox = blockIdx.x * 32 + threadIdx.x;
+  const int oy = blockIdx.y * 8 + threadIdx.y;
+  const int zc = blockIdx.z % g.nzc, bc0 = (blockIdx.z / g.nzc) * NC;
   if (ox >= g.mx.out || oy >= g.my.out) return;
   int y0, y1, x0, x1;
   float ly0, ly1, lx0, lx1;
   src_index(g.my, oy, y0, y1, ly0, ly1);
   src_index(g.mx, ox, x0, x1, lx0, lx1);
-  const float* xb = x + (size_t)bc * g.mz.in * g.my.in * g.mx.in;
-  size_t sH = (size_t)g.mx.in, sD = (size_t)g.my.in * g.mx.in;
-  float pre = g.pre;
-  auto row = [&](int z, int y) {
-    const float* r = xb + z * sD + y * sH;
-    return __fmul_rn(__ldg(r + x0), pre) * lx0 + __fmul_rn(__ldg(r + x1), pre) * lx1;
-  };
-#pragma unroll
-  for (int zz = 0; zz < RS_ZPB; ++zz) {
-    const int oz = oz0 + zz;
-    if (oz >= g.mz.out) break;
+  const size_t sD = (size_t)g.my.in * g.mx.in, cin = sD * g.mz.in;
+  const size_t oHW = (size_t)g.my.out * g.mx.out, cout = oHW * g.mz.out;
+  const float* xb = x + (size_t)bc0 * cin;
+  float* ob = out + (size_t)bc0 * cout + (size_t)oy * g.mx.out + ox;
+  const int o00 = y0 * g.mx.in + x0, o01 = y0 * g.mx.in + x1, o10 = y1 * g.mx.in + x0, o11 = y1 * g.mx.in + x1;
+  const int oz_begin = zc * g.zchunk, oz_end = min(oz_begin + g.zchunk, g.mz.out);
+  int cz0 = -2;          // source plane held in P0 (P1 holds cz0 + 1 when cz1 says so)
+  int cz1 = -2;
+  float P0[NC], P1[NC];
+  for (int oz = oz_begin; oz < oz_end; ++oz) {
     int z0, z1;
     float lz0, lz1;
     src_index(g.mz, oz, z0, z1, lz0, lz1);
-    float p0 = row(z0, y0) * ly0 + row(z0, y1) * ly1;
-    float v;
-    if (z1 != z0 || g.mz.in != g.mz.out) {
-      float p1 = row(z1, y0) * ly0 + row(z1, y1) * ly1;
-      v = p0 * lz0 + p1 * lz1;
-    } else {
-      v = p0;  // l0 = 1, l1 = 0
+    if (z0 != cz0) {
+      if (z0 == cz1) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) P0[c] = P1[c];
+      } else {
+        plane_xy<NC>(xb + (size_t)z0 * sD, cin, o00, o01, o10, o11, lx0, lx1, ly0, ly1, P0);
+      }
+      cz0 = z0;
+      cz1 = -2;
     }
-    out[(((size_t)bc * g.mz.out + oz) * g.my.out + oy) * g.mx.out + ox] = v * g.post;
+    if (z1 != z0 && z1 != cz1) {
+      plane_xy<NC>(xb + (size_t)z1 * sD, cin, o00, o01, o10, o11, lx0, lx1, ly0, ly1, P1);
+      cz1 = z1;
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const float v = (z1 != z0) ? P0[c] * lz0 + P1[c] * lz1 : P0[c];
+      ob[(size_t)c * cout + (size_t)oz * oHW] = v * g.scale;
+    }
   }
 }
 
@@ -99,58 +131,105 @@ __device__ __forceinline__ void adj_range(const AxisMap& m, int i, int& lo, int&
   hi = min(m.out - 1, (int)ceilf((float)(i + 1) * inv) + 1);
 }
 
-// Table-driven adjoint: each block first tabulates, for its 32 x 8 x 1 input indices, the (output index, weight)
-// pairs of the 1-D adjoint along every axis (at most ADJ_MAX per index), then every thread runs a pure
-// multiply-add loop over the outer product of its three short lists.
-constexpr int ADJ_MAX = 8;
+// The outputs whose stencil touches input index i form a contiguous range: first output + up to ADJ_L weights.
+constexpr int ADJ_L = 6;
 struct AdjList {
-  int n;
-  int o[ADJ_MAX];
-  float w[ADJ_MAX];
+  int lo, n;
+  float w[ADJ_L];
 };
-
-constexpr int ADJ_ZPB = 8;   // input slices per block: the x / y tables are built once and reused
-__global__ void __launch_bounds__(256) resize_bwd_table_kernel(const float* __restrict__ gout, float* __restrict__ gx, ResizeGeom g) {
-  __shared__ AdjList lx[32], ly[8], lz[ADJ_ZPB];
-  const int tid = threadIdx.y * 32 + threadIdx.x;
-  const int ix = blockIdx.x * 32 + threadIdx.x;
-  const int iy = blockIdx.y * 8 + threadIdx.y;
-  const int nzb = (g.mz.in + ADJ_ZPB - 1) / ADJ_ZPB;
-  const int iz0 = (blockIdx.z % nzb) * ADJ_ZPB, bc = blockIdx.z / nzb;
-  if (tid < 40 + ADJ_ZPB) {
-    const AxisMap& m = tid < 32 ? g.mx : (tid < 40 ? g.my : g.mz);
-    const int i = tid < 32 ? blockIdx.x * 32 + tid : (tid < 40 ? blockIdx.y * 8 + (tid - 32) : iz0 + (tid - 40));
-    AdjList& L = tid < 32 ? lx[tid] : (tid < 40 ? ly[tid - 32] : lz[tid - 40]);
-    L.n = 0;
-    if (i < m.in) {
-      int lo, hi;
-      adj_range(m, i, lo, hi);
-      for (int o = lo; o <= hi; ++o) {
-        float w = adj_weight(m, i, o);
-        if (w != 0.f && L.n < ADJ_MAX) { L.o[L.n] = o; L.w[L.n] = w; ++L.n; }
-      }
+__device__ __forceinline__ void make_adj(const AxisMap& m, int i, AdjList& L) {
+  int lo, hi;
+  adj_range(m, i, lo, hi);
+  L.lo = lo; L.n = 0;
+#pragma unroll
+  for (int k = 0; k < ADJ_L; ++k) L.w[k] = 0.f;
+  bool started = false;
+  for (int o = lo; o <= hi; ++o) {
+    const float w = adj_weight(m, i, o);
+    if (!started) {
+      if (w == 0.f) continue;
+      started = true;
+      L.lo = o;
     }
-  }
-  __syncthreads();
-  if (ix >= g.mx.in || iy >= g.my.in) return;
-  const AdjList& X = lx[threadIdx.x];
-  const AdjList& Y = ly[threadIdx.y];
-  const float* gb = gout + (size_t)bc * g.mz.out * g.my.out * g.mx.out;
-  for (int zz = 0; zz < ADJ_ZPB && iz0 + zz < g.mz.in; ++zz) {
-    const AdjList& Z = lz[zz];
-    float acc = 0.f;
-    for (int a = 0; a < Z.n; ++a) {
-      for (int b = 0; b < Y.n; ++b) {
-        const float* r = gb + ((size_t)Z.o[a] * g.my.out + Y.o[b]) * g.mx.out;
-        float racc = 0.f;
-        for (int c = 0; c < X.n; ++c) racc += X.w[c] * __ldg(r + X.o[c]);
-        acc += Z.w[a] * Y.w[b] * racc;
-      }
+    const int k = o - L.lo;
+    if (k < ADJ_L) {
+      // static indexing keeps the list in registers
+#pragma unroll
+      for (int q = 0; q < ADJ_L; ++q) if (q == k) L.w[q] = w;
+      if (w != 0.f) L.n = k + 1;
     }
-    gx[(((size_t)bc * g.mz.in + iz0 + zz) * g.my.in + iy) * g.mx.in + ix] = acc * (g.pre * g.post);
   }
 }
 
+template <int NC>
+__global__ void __launch_bounds__(256) resize_bwd_march_kernel(const float* __restrict__ gout, float* __restrict__ gx, ResizeGeom g) {
+  const int ix = blockIdx.x * 32 + threadIdx.x;
+  const int iy = blockIdx.y * 8 + threadIdx.y;
+  const int zc = blockIdx.z % g.nzc, bc0 = (blockIdx.z / g.nzc) * NC;
+  if (ix >= g.mx.in || iy >= g.my.in) return;
+  AdjList X, Y;
+  make_adj(g.mx, ix, X);
+  make_adj(g.my, iy, Y);
+  const size_t oHW = (size_t)g.my.out * g.mx.out, cout = oHW * g.mz.out;
+  const size_t iHW = (size_t)g.my.in * g.mx.in, cin = iHW * g.mz.in;
+  const float* gb = gout + (size_t)bc0 * cout + (size_t)Y.lo * g.mx.out + X.lo;
+  float* ob = gx + (size_t)bc0 * cin + (size_t)iy * g.mx.in + ix;
+  const int iz_begin = zc * g.zchunk, iz_end = min(iz_begin + g.zchunk, g.mz.in);
+  int oz_lo, oz_hi, t;
+  adj_range(g.mz, iz_begin, oz_lo, t);
+  adj_range(g.mz, iz_end - 1, t, oz_hi);
+  float A0[NC], A1[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) A0[c] = A1[c] = 0.f;
+  int zcur = iz_begin;           // A0 accumulates input slice zcur, A1 slice zcur + 1
+  auto flush = [&]() {
+    if (zcur < iz_end) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) ob[(size_t)c * cin + (size_t)zcur * iHW] = A0[c] * g.scale;
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { A0[c] = A1[c]; A1[c] = 0.f; }
+    ++zcur;
+  };
+  for (int oz = oz_lo; oz <= oz_hi; ++oz) {
+    int z0, z1;
+    float lz0, lz1;
+    src_index(g.mz, oz, z0, z1, lz0, lz1);
+    if (z1 < iz_begin || z0 >= iz_end) continue;
+    while (zcur < z0 && zcur < iz_end) flush();
+    // x / y reduction of this output plane over the adjoint lists
+    float R[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) R[c] = 0.f;
+    const float* pl = gb + (size_t)oz * oHW;
+#pragma unroll
+    for (int b = 0; b < ADJ_L; ++b) {
+      if (b < Y.n) {
+        float racc[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) racc[c] = 0.f;
+#pragma unroll
+        for (int a = 0; a < ADJ_L; ++a) {
+          if (a < X.n) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) racc[c] += X.w[a] * __ldg(pl + (size_t)c * cout + b * g.mx.out + a);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) R[c] += Y.w[b] * racc[c];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      if (z0 == zcur) A0[c] += lz0 * R[c];
+      if (z1 == zcur) A0[c] += lz1 * R[c];
+      else if (z1 == zcur + 1) A1[c] += lz1 * R[c];
+    }
+  }
+  while (zcur < iz_end) flush();
+}
+
+// generic fallback (any ratio): one thread per input voxel, weights recomputed in the loops
 __global__ void __launch_bounds__(256) resize_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gx, ResizeGeom g) {
   int ix = blockIdx.x * 32 + threadIdx.x;
   int iy = blockIdx.y * 8 + threadIdx.y;
@@ -177,7 +256,7 @@ __global__ void __launch_bounds__(256) resize_bwd_kernel(const float* __restrict
       acc += wz * wy * racc;
     }
   }
-  gx[(((size_t)bc * g.mz.in + iz) * g.my.in + iy) * g.mx.in + ix] = acc * (g.pre * g.post);
+  gx[(((size_t)bc * g.mz.in + iz) * g.my.in + iy) * g.mx.in + ix] = acc * g.scale;
 }
 
 }  // namespace vxm
@@ -187,17 +266,24 @@ using namespace vxm;
 static int resize_check(int B, int C, int Di, int Hi, int Wi, int Do, int Ho, int Wo) {
   VXM_REQUIRE(B > 0 && C > 0 && Di > 0 && Hi > 0 && Wi > 0 && Do > 0 && Ho > 0 && Wo > 0, "resize: non-positive dimension");
   VXM_REQUIRE((size_t)B * C * (Di > Do ? Di : Do) <= 65535u, "resize: B*C*D exceeds the launch grid limit");
+  VXM_REQUIRE((size_t)Di * Hi * Wi < (1u << 31) && (size_t)Do * Ho * Wo < (1u << 31), "resize: volume exceeds 2^31 voxels");
   return VXM_OK;
 }
+
+static int channels_per_thread(int BC) { return BC % 3 == 0 ? 3 : (BC % 2 == 0 ? 2 : 1); }
 
 extern "C" int vxm_resize_fwd(const float* x, float* out, int B, int C, int Di, int Hi, int Wi, int Do,
                               int Ho, int Wo, float pre, float post, void* stream) {
   int rc = resize_check(B, C, Di, Hi, Wi, Do, Ho, Wo);
   if (rc) return rc;
   VXM_REQUIRE(x && out, "resize_fwd: null pointer");
-  ResizeGeom g{make_map(Di, Do), make_map(Hi, Ho), make_map(Wi, Wo), B * C, pre, post};
-  dim3 block(32, 8, 1), grid((Wo + 31) / 32, (Ho + 7) / 8, ((Do + RS_ZPB - 1) / RS_ZPB) * B * C);
-  resize_fwd_kernel<<<grid, block, 0, as_stream(stream)>>>(x, out, g);
+  ResizeGeom g{make_map(Di, Do), make_map(Hi, Ho), make_map(Wi, Wo), B * C, RS_ZCHUNK, (Do + RS_ZCHUNK - 1) / RS_ZCHUNK, pre * post};
+  const int nc = channels_per_thread(B * C);
+  dim3 block(32, 8, 1), grid((Wo + 31) / 32, (Ho + 7) / 8, g.nzc * (B * C / nc));
+  cudaStream_t st = as_stream(stream);
+  if (nc == 3) resize_fwd_kernel<3><<<grid, block, 0, st>>>(x, out, g);
+  else if (nc == 2) resize_fwd_kernel<2><<<grid, block, 0, st>>>(x, out, g);
+  else resize_fwd_kernel<1><<<grid, block, 0, st>>>(x, out, g);
   return check_launch("resize_fwd");
 }
 
@@ -206,13 +292,19 @@ extern "C" int vxm_resize_bwd(const float* grad_out, float* grad_x, int B, int C
   int rc = resize_check(B, C, Di, Hi, Wi, Do, Ho, Wo);
   if (rc) return rc;
   VXM_REQUIRE(grad_out && grad_x, "resize_bwd: null pointer");
-  ResizeGeom g{make_map(Di, Do), make_map(Hi, Ho), make_map(Wi, Wo), B * C, pre, post};
-  dim3 block(32, 8, 1), grid((Wi + 31) / 32, (Hi + 7) / 8, Di * B * C);
-  auto fits = [](const AxisMap& m) { return m.in == m.out || (m.ratio > 0.f && 2.0f / m.ratio + 5.0f <= (float)ADJ_MAX + 2.f); };
+  ResizeGeom g{make_map(Di, Do), make_map(Hi, Ho), make_map(Wi, Wo), B * C, RS_ZCHUNK, (Di + RS_ZCHUNK - 1) / RS_ZCHUNK, pre * post};
+  cudaStream_t st = as_stream(stream);
+  // an input index is touched by at most ~2/ratio + 1 outputs; the marching kernel keeps ADJ_L of them in registers
+  auto fits = [](const AxisMap& m) { return m.in == m.out || (m.ratio > 0.f && 2.0f / m.ratio + 1.5f <= (float)ADJ_L); };
   if (fits(g.mz) && fits(g.my) && fits(g.mx)) {
-    dim3 gridt((Wi + 31) / 32, (Hi + 7) / 8, ((Di + ADJ_ZPB - 1) / ADJ_ZPB) * B * C);
-    resize_bwd_table_kernel<<<gridt, block, 0, as_stream(stream)>>>(grad_out, grad_x, g);
+    const int nc = channels_per_thread(B * C);
+    dim3 block(32, 8, 1), grid((Wi + 31) / 32, (Hi + 7) / 8, g.nzc * (B * C / nc));
+    if (nc == 3) resize_bwd_march_kernel<3><<<grid, block, 0, st>>>(grad_out, grad_x, g);
+    else if (nc == 2) resize_bwd_march_kernel<2><<<grid, block, 0, st>>>(grad_out, grad_x, g);
+    else resize_bwd_march_kernel<1><<<grid, block, 0, st>>>(grad_out, grad_x, g);
+  } else {
+    dim3 block(32, 8, 1), grid((Wi + 31) / 32, (Hi + 7) / 8, Di * B * C);
+    resize_bwd_kernel<<<grid, block, 0, st>>>(grad_out, grad_x, g);
   }
-  else resize_bwd_kernel<<<grid, block, 0, as_stream(stream)>>>(grad_out, grad_x, g);
   return check_launch("resize_bwd");
 }

@@ -170,6 +170,232 @@ __global__ void __launch_bounds__(256) vecint_bwd_kernel(const float* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// FAST path (arith == VXM_ARITH_FAST, 3-D): same algorithm, but
+//  * the field lives in an INTERLEAVED float4 (z, y, x, 0) layout inside the launch: a squaring step is one
+//    16-byte own load, eight 16-byte gathers and one 16-byte store per voxel instead of 3 + 24 + 3 four-byte
+//    accesses (the planar layout is only read in the scaling pass and written by the last step);
+//  * coordinates are p + v directly (no replay of the reference's normalise / un-normalise round trip), the blend
+//    is a lerp tree, interior voxels take a predicate-free branch (see warp.cu);
+//  * the backward scatters d/d(src) with ONE red.global.add.v4.f32 per corner (8 + 1 vector reductions per voxel
+//    and step instead of 24 scalar atomics), rotating three float4 gradient buffers so that every step is one
+//    phase (one grid.sync) instead of two.
+// Agreement with the exact path: ~1e-6 of the field's range per step (tests/test_gpu_ops.py).
+// ------------------------------------------------------------------------------------------------------------
+struct FastDiv {
+  unsigned mul, shr;
+  int d;
+};
+static FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = d;
+  if (d == 1) { f.mul = 0; f.shr = 0; return f; }
+  unsigned lg = 0;
+  while ((1u << lg) < (unsigned)d) ++lg;
+  const unsigned p = 31 + lg;
+  f.mul = (unsigned)(((1ull << p) + (unsigned)d - 1) / (unsigned)d);
+  f.shr = p - 32;
+  return f;
+}
+__device__ __forceinline__ int fdiv(int n, const FastDiv& f) { return f.d == 1 ? n : (int)(__umulhi((unsigned)n, f.mul) >> f.shr); }
+
+struct VecFast {
+  int B, D, H, W, HW, DHW, nvox;
+  FastDiv dW, dH, dD;
+};
+
+struct Corner8 {
+  bool interior;
+  int base;            // interior: offset of corner (z0,y0,x0)
+  int off[8];          // border: clamped offsets
+  float w[8];          // border: weights (0 outside the volume)
+  unsigned ok;         // border: bit k set <=> corner k inside the volume
+  float tx, ty, tz;
+};
+
+__device__ __forceinline__ void corners_fast(float cz, float cy, float cx, const VecFast& g, Corner8& c) {
+  const float fx = floorf(cx), fy = floorf(cy), fz = floorf(cz);
+  const int x0 = f2i(fx), y0 = f2i(fy), z0 = f2i(fz);
+  c.tx = cx - fx; c.ty = cy - fy; c.tz = cz - fz;
+  c.interior = (unsigned)x0 < (unsigned)(g.W - 1) && (unsigned)y0 < (unsigned)(g.H - 1) && (unsigned)z0 < (unsigned)(g.D - 1);
+  c.base = (z0 * g.H + y0) * g.W + x0;
+  if (!c.interior) {
+    const float wx[2] = {(unsigned)x0 < (unsigned)g.W ? 1.f - c.tx : 0.f, (unsigned)(x0 + 1) < (unsigned)g.W ? c.tx : 0.f};
+    const float wy[2] = {(unsigned)y0 < (unsigned)g.H ? 1.f - c.ty : 0.f, (unsigned)(y0 + 1) < (unsigned)g.H ? c.ty : 0.f};
+    const float wz[2] = {(unsigned)z0 < (unsigned)g.D ? 1.f - c.tz : 0.f, (unsigned)(z0 + 1) < (unsigned)g.D ? c.tz : 0.f};
+    const int xo[2] = {min(max(x0, 0), g.W - 1), min(max(x0 + 1, 0), g.W - 1)};
+    const int yo[2] = {min(max(y0, 0), g.H - 1) * g.W, min(max(y0 + 1, 0), g.H - 1) * g.W};
+    const int zo[2] = {min(max(z0, 0), g.D - 1) * g.HW, min(max(z0 + 1, 0), g.D - 1) * g.HW};
+    const bool vx[2] = {(unsigned)x0 < (unsigned)g.W, (unsigned)(x0 + 1) < (unsigned)g.W};
+    const bool vy[2] = {(unsigned)y0 < (unsigned)g.H, (unsigned)(y0 + 1) < (unsigned)g.H};
+    const bool vz[2] = {(unsigned)z0 < (unsigned)g.D, (unsigned)(z0 + 1) < (unsigned)g.D};
+    c.ok = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      c.off[k] = zo[k >> 2] + yo[(k >> 1) & 1] + xo[k & 1];
+      c.w[k] = wz[k >> 2] * wy[(k >> 1) & 1] * wx[k & 1];
+      c.ok |= (vz[k >> 2] && vy[(k >> 1) & 1] && vx[k & 1]) ? (1u << k) : 0u;
+    }
+  }
+}
+
+__device__ __forceinline__ float4 lerp4(const float4& a, const float4& b, float t) {
+  return make_float4(fmaf(t, b.x - a.x, a.x), fmaf(t, b.y - a.y, a.y), fmaf(t, b.z - a.z, a.z), 0.f);
+}
+
+// SAVE: every intermediate field v_0 .. v_{n-1} is kept (states, for the backward); otherwise two buffers ping-pong
+template <bool SAVE>
+__global__ void __launch_bounds__(512) vecint_fwd_fast_kernel(const float* __restrict__ vel, float* __restrict__ out, float4* buf,
+                                                              VecFast g, int nsteps, float scale) {
+  cg::grid_group grid = cg::this_grid();
+  const int tid0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const int stride = gridDim.x * blockDim.x;
+  auto field = [&](int k) -> float4* { return buf + (size_t)(SAVE ? k : (k & 1)) * g.nvox; };
+  {
+    float4* f0 = field(0);
+    for (int q = tid0; q < g.nvox; q += stride) {
+      const int b = q / g.DHW;
+      const int p = q - b * g.DHW;
+      const float* vb = vel + (size_t)b * 3 * g.DHW + p;
+      f0[q] = make_float4(__ldg(vb) * scale, __ldg(vb + g.DHW) * scale, __ldg(vb + 2 * g.DHW) * scale, 0.f);
+    }
+  }
+  grid.sync();
+  for (int s = 0; s < nsteps; ++s) {
+    const float4* cur = field(s);
+    float4* nxt = field(s + 1);
+    const bool last = s + 1 == nsteps;
+    for (int q = tid0; q < g.nvox; q += stride) {
+      const int t1 = fdiv(q, g.dW), x = q - t1 * g.W;
+      const int t2 = fdiv(t1, g.dH), y = t1 - t2 * g.H;
+      const int b = fdiv(t2, g.dD), z = t2 - b * g.D;
+      const float4* cb = cur + (size_t)b * g.DHW;
+      const float4 v = cur[q];
+      Corner8 c;
+      corners_fast((float)z + v.x, (float)y + v.y, (float)x + v.z, g, c);
+      float4 r;
+      if (c.interior) {
+        const float4* s0 = cb + c.base;
+        const float4 a00 = s0[0], a01 = s0[1], a10 = s0[g.W], a11 = s0[g.W + 1];
+        const float4 b00 = s0[g.HW], b01 = s0[g.HW + 1], b10 = s0[g.HW + g.W], b11 = s0[g.HW + g.W + 1];
+        const float4 ra = lerp4(lerp4(a00, a01, c.tx), lerp4(a10, a11, c.tx), c.ty);
+        const float4 rb = lerp4(lerp4(b00, b01, c.tx), lerp4(b10, b11, c.tx), c.ty);
+        r = lerp4(ra, rb, c.tz);
+      } else {
+        r = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float4 u = cb[c.off[k]];
+          r.x = fmaf(c.w[k], u.x, r.x); r.y = fmaf(c.w[k], u.y, r.y); r.z = fmaf(c.w[k], u.z, r.z);
+        }
+      }
+      const float4 o = make_float4(v.x + r.x, v.y + r.y, v.z + r.z, 0.f);
+      if (last) {
+        const int p = q - b * g.DHW;
+        float* ob = out + (size_t)b * 3 * g.DHW + p;
+        ob[0] = o.x; ob[g.DHW] = o.y; ob[2 * g.DHW] = o.z;
+      } else {
+        nxt[q] = o;
+      }
+    }
+    if (!last) grid.sync();
+  }
+}
+
+// three rotating float4 gradient buffers G[0..2] (work): step j reads G[j%3], reduces into G[(j+1)%3] (zero on entry)
+// and zeroes G[(j+2)%3] for the step after.
+__global__ void __launch_bounds__(512) vecint_bwd_fast_kernel(const float* __restrict__ gout, const float4* __restrict__ states,
+                                                              float* __restrict__ grad_vel, float4* G, VecFast g, int nsteps, float scale) {
+  cg::grid_group grid = cg::this_grid();
+  const int tid0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const int stride = gridDim.x * blockDim.x;
+  float4* G0 = G;
+  float4* G1 = G + (size_t)g.nvox;
+  float4* G2 = G + 2 * (size_t)g.nvox;
+  for (int q = tid0; q < g.nvox; q += stride) {
+    const int b = q / g.DHW, p = q - b * g.DHW;
+    const float* gb = gout + (size_t)b * 3 * g.DHW + p;
+    G0[q] = make_float4(__ldg(gb), __ldg(gb + g.DHW), __ldg(gb + 2 * g.DHW), 0.f);
+    G1[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  grid.sync();
+  for (int j = 0; j < nsteps; ++j) {
+    const int k = nsteps - 1 - j;
+    const float4* v = states + (size_t)k * g.nvox;
+    const float4* gn = j % 3 == 0 ? G0 : (j % 3 == 1 ? G1 : G2);
+    float4* gc = j % 3 == 0 ? G1 : (j % 3 == 1 ? G2 : G0);
+    float4* gz = j % 3 == 0 ? G2 : (j % 3 == 1 ? G0 : G1);
+    for (int q = tid0; q < g.nvox; q += stride) {
+      const int t1 = fdiv(q, g.dW), x = q - t1 * g.W;
+      const int t2 = fdiv(t1, g.dH), y = t1 - t2 * g.H;
+      const int b = fdiv(t2, g.dD), z = t2 - b * g.D;
+      const float4* vb = v + (size_t)b * g.DHW;
+      float4* gcb = gc + (size_t)b * g.DHW;
+      const float4 own = v[q];
+      const float4 go = gn[q];
+      gz[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      Corner8 c;
+      corners_fast((float)z + own.x, (float)y + own.y, (float)x + own.z, g, c);
+      float dz, dy, dx;
+      if (c.interior) {
+        const float4* s0 = vb + c.base;
+        float4* t0 = gcb + c.base;
+        const float4 a00 = s0[0], a01 = s0[1], a10 = s0[g.W], a11 = s0[g.W + 1];
+        const float4 b00 = s0[g.HW], b01 = s0[g.HW + 1], b10 = s0[g.HW + g.W], b11 = s0[g.HW + g.W + 1];
+        // <corner, go>: the scalar field whose position-gradient is the flow gradient of this voxel
+        auto dot = [&](const float4& u) { return fmaf(u.x, go.x, fmaf(u.y, go.y, u.z * go.z)); };
+        const float s000 = dot(a00), s001 = dot(a01), s010 = dot(a10), s011 = dot(a11);
+        const float s100 = dot(b00), s101 = dot(b01), s110 = dot(b10), s111 = dot(b11);
+        const float ra0 = fmaf(c.tx, s001 - s000, s000), ra1 = fmaf(c.tx, s011 - s010, s010);
+        const float rb0 = fmaf(c.tx, s101 - s100, s100), rb1 = fmaf(c.tx, s111 - s110, s110);
+        const float dxa = fmaf(c.ty, (s011 - s010) - (s001 - s000), s001 - s000), dxb = fmaf(c.ty, (s111 - s110) - (s101 - s100), s101 - s100);
+        dx = fmaf(c.tz, dxb - dxa, dxa);
+        const float dya = ra1 - ra0, dyb = rb1 - rb0;
+        dy = fmaf(c.tz, dyb - dya, dya);
+        dz = fmaf(c.ty, rb1 - rb0, rb0) - fmaf(c.ty, ra1 - ra0, ra0);
+        const float wx0 = 1.f - c.tx, wy0 = 1.f - c.ty, wz0 = 1.f - c.tz;
+        auto red = [&](float4* t, float w) { atomicAdd(t, make_float4(w * go.x, w * go.y, w * go.z, 0.f)); };
+        red(t0, wz0 * wy0 * wx0); red(t0 + 1, wz0 * wy0 * c.tx);
+        red(t0 + g.W, wz0 * c.ty * wx0); red(t0 + g.W + 1, wz0 * c.ty * c.tx);
+        red(t0 + g.HW, c.tz * wy0 * wx0); red(t0 + g.HW + 1, c.tz * wy0 * c.tx);
+        red(t0 + g.HW + g.W, c.tz * c.ty * wx0); red(t0 + g.HW + g.W + 1, c.tz * c.ty * c.tx);
+      } else {
+        // border: only in-volume corners carry a value (zeros padding) and receive gradient
+        const float fx = c.tx, fy = c.ty, fz = c.tz;
+        dz = dy = dx = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (c.ok & (1u << k)) {
+            const float4 u = vb[c.off[k]];
+            const float sk = fmaf(u.x, go.x, fmaf(u.y, go.y, u.z * go.z));
+            const float wx = (k & 1) ? fx : 1.f - fx, wy = (k & 2) ? fy : 1.f - fy, wz = (k & 4) ? fz : 1.f - fz;
+            dx += ((k & 1) ? sk : -sk) * wy * wz;
+            dy += ((k & 2) ? sk : -sk) * wx * wz;
+            dz += ((k & 4) ? sk : -sk) * wx * wy;
+            atomicAdd(gcb + c.off[k], make_float4(c.w[k] * go.x, c.w[k] * go.y, c.w[k] * go.z, 0.f));
+          }
+        }
+      }
+      atomicAdd(gc + q, make_float4(go.x + dz, go.y + dy, go.z + dx, 0.f));
+    }
+    grid.sync();
+  }
+  const float4* Gf = nsteps % 3 == 0 ? G0 : (nsteps % 3 == 1 ? G1 : G2);
+  for (int q = tid0; q < g.nvox; q += stride) {
+    const int b = q / g.DHW, p = q - b * g.DHW;
+    const float4 r = Gf[q];
+    float* o = grad_vel + (size_t)b * 3 * g.DHW + p;
+    o[0] = r.x * scale; o[g.DHW] = r.y * scale; o[2 * g.DHW] = r.z * scale;
+  }
+}
+
+static VecFast make_vfast(int B, int D, int H, int W) {
+  VecFast g;
+  g.B = B; g.D = D; g.H = H; g.W = W; g.HW = H * W; g.DHW = D * H * W; g.nvox = B * D * H * W;
+  g.dW = make_fastdiv(W); g.dH = make_fastdiv(H); g.dD = make_fastdiv(D);
+  return g;
+}
+
 static VecGeom make_vgeom(int B, int D, int H, int W, int nd) {
   VecGeom g;
   g.vol = make_vol(D, H, W);
@@ -207,6 +433,73 @@ extern "C" size_t vxm_vecint_workspace_bytes(int B, int D, int H, int W, int nd,
   return (size_t)B * nd * D * H * W * sizeof(float);
 }
 
+extern "C" size_t vxm_vecint_fast_states_bytes(int B, int D, int H, int W, int nsteps) {
+  return (size_t)(nsteps > 0 ? nsteps : 0) * B * D * H * W * sizeof(float4);
+}
+extern "C" size_t vxm_vecint_fast_work_bytes(int B, int D, int H, int W, int backward) {
+  return (size_t)(backward ? 3 : 2) * B * D * H * W * sizeof(float4);
+}
+
+template <typename K>
+static int coop_grid_fast(K kernel, int threads, int* grid_out) {
+  int dev = 0, nsm = 0, coop = 0, per_sm = 0;
+  VXM_CUDA(cudaGetDevice(&dev));
+  VXM_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  VXM_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  VXM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
+  if (!coop || per_sm < 1) {
+    set_error("vecint: cooperative launch unavailable on this device");
+    return VXM_ERR_UNSUPPORTED;
+  }
+  *grid_out = nsm * per_sm;
+  return VXM_OK;
+}
+
+static int vecint_fast_check(int B, int D, int H, int W, int nd, int nsteps) {
+  VXM_REQUIRE(nd == 3, "vecint (fast): 3-D fields only");
+  VXM_REQUIRE(nsteps >= 1 && nsteps < 31, "vecint (fast): nsteps must be in 1..30, found: %d", nsteps);
+  VXM_REQUIRE(B > 0 && D > 1 && H > 1 && W > 1, "vecint (fast): every spatial size must be > 1");
+  VXM_REQUIRE((size_t)B * D * H * W < (1u << 30), "vecint (fast): field exceeds 2^30 voxels");
+  return VXM_OK;
+}
+
+static int vecint_fwd_fast(const float* vel, float* out, void* states, void* work, int B, int D, int H, int W, int nd, int nsteps, cudaStream_t st) {
+  int rc = vecint_fast_check(B, D, H, W, nd, nsteps);
+  if (rc) return rc;
+  VXM_REQUIRE(states || work, "vecint_fwd (fast): need `states` or `work`");
+  VecFast g = make_vfast(B, D, H, W);
+  float scale = 1.0f / (float)(1u << nsteps);
+  float4* buf = (float4*)(states ? states : work);
+  int grid = 0;
+  void* args[] = {(void*)&vel, (void*)&out, (void*)&buf, (void*)&g, (void*)&nsteps, (void*)&scale};
+  if (states) {
+    rc = coop_grid_fast(vecint_fwd_fast_kernel<true>, 512, &grid);
+    if (rc) return rc;
+    VXM_CUDA(cudaLaunchCooperativeKernel((void*)vecint_fwd_fast_kernel<true>, dim3(grid), dim3(512), args, 0, st));
+  } else {
+    rc = coop_grid_fast(vecint_fwd_fast_kernel<false>, 512, &grid);
+    if (rc) return rc;
+    VXM_CUDA(cudaLaunchCooperativeKernel((void*)vecint_fwd_fast_kernel<false>, dim3(grid), dim3(512), args, 0, st));
+  }
+  return check_launch("vecint_fwd");
+}
+
+static int vecint_bwd_fast(const float* gout, const void* states, float* grad_vel, void* work, int B, int D, int H, int W, int nd, int nsteps, cudaStream_t st) {
+  int rc = vecint_fast_check(B, D, H, W, nd, nsteps);
+  if (rc) return rc;
+  VXM_REQUIRE(states && work, "vecint_bwd (fast): need `states` and `work`");
+  VecFast g = make_vfast(B, D, H, W);
+  float scale = 1.0f / (float)(1u << nsteps);
+  const float4* sp = (const float4*)states;
+  float4* G = (float4*)work;
+  int grid = 0;
+  rc = coop_grid_fast(vecint_bwd_fast_kernel, 512, &grid);
+  if (rc) return rc;
+  void* args[] = {(void*)&gout, (void*)&sp, (void*)&grad_vel, (void*)&G, (void*)&g, (void*)&nsteps, (void*)&scale};
+  VXM_CUDA(cudaLaunchCooperativeKernel((void*)vecint_bwd_fast_kernel, dim3(grid), dim3(512), args, 0, st));
+  return check_launch("vecint_bwd");
+}
+
 template <bool IS3D, int ARITH>
 static int vecint_fwd_launch(const float* vel, float* out, float* states, float* work, VecGeom g,
                              int nsteps, float scale, cudaStream_t st) {
@@ -229,6 +522,7 @@ extern "C" int vxm_vecint_fwd(const float* vel, float* out, float* states, void*
   VXM_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "vecint: non-positive dimension");
   VXM_REQUIRE(nd == 3 || D == 1, "vecint: a 2-D problem must be passed with D == 1");
   VXM_REQUIRE(states || work || nsteps == 0, "vecint_fwd: need `states` or `work`");
+  if (arith == VXM_ARITH_FAST) return vecint_fwd_fast(vel, out, states, work, B, D, H, W, nd, nsteps, as_stream(stream));
   VecGeom g = make_vgeom(B, D, H, W, nd);
   float scale = 1.0f / (float)(1u << nsteps);
   cudaStream_t st = as_stream(stream);
@@ -263,6 +557,7 @@ extern "C" int vxm_vecint_bwd(const float* grad_out, const float* states, float*
   VXM_REQUIRE(grad_out && grad_vel, "vecint_bwd: null pointer");
   VXM_REQUIRE(nsteps == 0 || (states && work), "vecint_bwd: need `states` and `work`");
   VXM_REQUIRE(nd == 3 || D == 1, "vecint: a 2-D problem must be passed with D == 1");
+  if (arith == VXM_ARITH_FAST) return vecint_bwd_fast(grad_out, states, grad_vel, work, B, D, H, W, nd, nsteps, as_stream(stream));
   VecGeom g = make_vgeom(B, D, H, W, nd);
   float scale = 1.0f / (float)(1u << nsteps);
   cudaStream_t st = as_stream(stream);

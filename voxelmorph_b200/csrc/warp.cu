@@ -120,6 +120,183 @@ __global__ void __launch_bounds__(TX* TY) warp_bwd_kernel(const float* __restric
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// FAST linear path (arith == VXM_ARITH_FAST).  north_star asks the linear resampler for 1e-4 relative accuracy,
+// not for a replay of torch's coordinate round trip (layers.py:37 + GridSampler.h:27-31), which costs a true
+// fp32 division and ~10 dependent roundings per axis and made the exact kernel instruction bound (336 executed
+// instructions per voxel, 15 % of HBM peak).  Here  coord = (p + flow) * (Ssrc-1)/(S-1)  (the same map in exact
+// arithmetic; identity scale when src and flow grids agree, which is the only case the reference uses), the
+// 8-corner blend is three nested lerps, and voxels whose stencil lies inside the volume (all but a one-voxel
+// shell for registration flows) take a branch with no per-corner predicates.  Each thread walks ZU consecutive
+// slices and issues all of their flow loads before the first gather so that enough bytes are in flight.
+// Deviation from the exact path: <= a few 1e-6 of the value range (tests/test_gpu_ops.py).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int ZU = 4;
+
+struct FastGeom {
+  int D, H, W, Ds, Hs, Ws, B, C, nd, nzc;
+  float rz, ry, rx;
+};
+
+template <bool IS3D>
+__device__ __forceinline__ float blend_fast(const float* __restrict__ plane, bool interior, int base, int sW, int sHW,
+                                            float tx, float ty, float tz, const Stencil8& st) {
+  if (interior) {
+    const float* s = plane + base;
+    const float a00 = __ldg(s), a01 = __ldg(s + 1), a10 = __ldg(s + sW), a11 = __ldg(s + sW + 1);
+    const float r0 = fmaf(tx, a01 - a00, a00), r1 = fmaf(tx, a11 - a10, a10);
+    float v0 = fmaf(ty, r1 - r0, r0);
+    if (IS3D) {
+      const float b00 = __ldg(s + sHW), b01 = __ldg(s + sHW + 1), b10 = __ldg(s + sHW + sW), b11 = __ldg(s + sHW + sW + 1);
+      const float q0 = fmaf(tx, b01 - b00, b00), q1 = fmaf(tx, b11 - b10, b10);
+      const float v1 = fmaf(ty, q1 - q0, q0);
+      v0 = fmaf(tz, v1 - v0, v0);
+    }
+    return v0;
+  }
+  return sample8<IS3D, true>(plane, st);
+}
+
+template <bool IS3D>
+__global__ void __launch_bounds__(TX* TY) warp_fwd_fast_kernel(const float* __restrict__ src, const float* __restrict__ flow,
+                                                               float* __restrict__ out, FastGeom g) {
+  const int x = blockIdx.x * TX + threadIdx.x;
+  const int y = blockIdx.y * TY + threadIdx.y;
+  const int zc = blockIdx.z % g.nzc, b = blockIdx.z / g.nzc;
+  if (x >= g.W || y >= g.H) return;
+  const int HW = g.H * g.W, DHW = g.D * HW;
+  const int sW = g.Ws, sHW = g.Hs * g.Ws, sDHW = g.Ds * sHW;
+  const float* fb = flow + (size_t)b * g.nd * DHW + y * g.W + x;
+  const float* sb = src + (size_t)b * g.C * sDHW;
+  float* ob = out + (size_t)b * g.C * DHW + y * g.W + x;
+  const int z0c = zc * ZU;
+  float f[ZU][3];
+#pragma unroll
+  for (int u = 0; u < ZU; ++u) {
+    const int z = z0c + u;
+    if (z < g.D) {
+      const float* q = fb + z * HW;
+      if (IS3D) { f[u][0] = __ldg(q); f[u][1] = __ldg(q + DHW); f[u][2] = __ldg(q + 2 * DHW); }
+      else { f[u][0] = 0.f; f[u][1] = __ldg(q); f[u][2] = __ldg(q + DHW); }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < ZU; ++u) {
+    const int z = z0c + u;
+    if (z >= g.D) break;
+    const float cz = IS3D ? ((float)z + f[u][0]) * g.rz : 0.f;
+    const float cy = ((float)y + f[u][1]) * g.ry;
+    const float cx = ((float)x + f[u][2]) * g.rx;
+    const float fx = floorf(cx), fy = floorf(cy), fz = floorf(cz);
+    const int x0 = f2i(fx), y0 = f2i(fy), zz0 = f2i(fz);
+    const bool interior = (unsigned)x0 < (unsigned)(g.Ws - 1) && (unsigned)y0 < (unsigned)(g.Hs - 1) &&
+                          (!IS3D || (unsigned)zz0 < (unsigned)(g.Ds - 1));
+    Stencil8 st;
+    if (!interior) make_stencil8<IS3D>(cx, cy, cz, g.Ds, g.Hs, g.Ws, st);
+    const int base = (zz0 * g.Hs + y0) * g.Ws + x0;
+    const float tx = cx - fx, ty = cy - fy, tz = cz - fz;
+    for (int c = 0; c < g.C; ++c)
+      ob[(size_t)c * DHW + z * HW] = blend_fast<IS3D>(sb + (size_t)c * sDHW, interior, base, sW, sHW, tx, ty, tz, st);
+  }
+}
+
+// backward of the fast path: d out / d flow from the same lerp tree (needs the 8 corner values once per channel),
+// d out / d src as a scatter (red.global.add) only when the caller asks for it.
+template <bool IS3D>
+__global__ void __launch_bounds__(TX* TY) warp_bwd_fast_kernel(const float* __restrict__ gout, const float* __restrict__ src,
+                                                               const float* __restrict__ flow, float* __restrict__ gsrc,
+                                                               float* __restrict__ gflow, FastGeom g) {
+  const int x = blockIdx.x * TX + threadIdx.x;
+  const int y = blockIdx.y * TY + threadIdx.y;
+  const int zc = blockIdx.z % g.nzc, b = blockIdx.z / g.nzc;
+  if (x >= g.W || y >= g.H) return;
+  const int HW = g.H * g.W, DHW = g.D * HW;
+  const int sW = g.Ws, sHW = g.Hs * g.Ws, sDHW = g.Ds * sHW;
+  const float* fb = flow + (size_t)b * g.nd * DHW + y * g.W + x;
+  const float* sb = src + (size_t)b * g.C * sDHW;
+  float* gsb = gsrc ? gsrc + (size_t)b * g.C * sDHW : nullptr;
+  const float* gob = gout + (size_t)b * g.C * DHW + y * g.W + x;
+  const int z0c = zc * ZU;
+  float f[ZU][3];
+#pragma unroll
+  for (int u = 0; u < ZU; ++u) {
+    const int z = z0c + u;
+    if (z < g.D) {
+      const float* q = fb + z * HW;
+      if (IS3D) { f[u][0] = __ldg(q); f[u][1] = __ldg(q + DHW); f[u][2] = __ldg(q + 2 * DHW); }
+      else { f[u][0] = 0.f; f[u][1] = __ldg(q); f[u][2] = __ldg(q + DHW); }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < ZU; ++u) {
+    const int z = z0c + u;
+    if (z >= g.D) break;
+    const float cz = IS3D ? ((float)z + f[u][0]) * g.rz : 0.f;
+    const float cy = ((float)y + f[u][1]) * g.ry;
+    const float cx = ((float)x + f[u][2]) * g.rx;
+    const float fx = floorf(cx), fy = floorf(cy), fz = floorf(cz);
+    const int x0 = f2i(fx), y0 = f2i(fy), zz0 = f2i(fz);
+    const float tx = cx - fx, ty = cy - fy, tz = IS3D ? cz - fz : 0.f;
+    // per-axis validity of the two taps (zeros padding): out-of-volume taps read as 0 and receive no gradient
+    const bool xa = (unsigned)x0 < (unsigned)g.Ws, xb = (unsigned)(x0 + 1) < (unsigned)g.Ws;
+    const bool ya = (unsigned)y0 < (unsigned)g.Hs, yb = (unsigned)(y0 + 1) < (unsigned)g.Hs;
+    const bool za = !IS3D || (unsigned)zz0 < (unsigned)g.Ds, zb = IS3D && (unsigned)(zz0 + 1) < (unsigned)g.Ds;
+    const int xo0 = min(max(x0, 0), g.Ws - 1), xo1 = min(max(x0 + 1, 0), g.Ws - 1);
+    const int yo0 = min(max(y0, 0), g.Hs - 1) * sW, yo1 = min(max(y0 + 1, 0), g.Hs - 1) * sW;
+    const int zo0 = IS3D ? min(max(zz0, 0), g.Ds - 1) * sHW : 0, zo1 = IS3D ? min(max(zz0 + 1, 0), g.Ds - 1) * sHW : 0;
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    for (int c = 0; c < g.C; ++c) {
+      const float go = __ldg(gob + (size_t)c * DHW + z * HW);
+      const float* s = sb + (size_t)c * sDHW;
+      const float a00 = (za && ya && xa) ? __ldg(s + zo0 + yo0 + xo0) : 0.f, a01 = (za && ya && xb) ? __ldg(s + zo0 + yo0 + xo1) : 0.f;
+      const float a10 = (za && yb && xa) ? __ldg(s + zo0 + yo1 + xo0) : 0.f, a11 = (za && yb && xb) ? __ldg(s + zo0 + yo1 + xo1) : 0.f;
+      float b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;
+      if (IS3D) {
+        b00 = (zb && ya && xa) ? __ldg(s + zo1 + yo0 + xo0) : 0.f; b01 = (zb && ya && xb) ? __ldg(s + zo1 + yo0 + xo1) : 0.f;
+        b10 = (zb && yb && xa) ? __ldg(s + zo1 + yo1 + xo0) : 0.f; b11 = (zb && yb && xb) ? __ldg(s + zo1 + yo1 + xo1) : 0.f;
+      }
+      if (gflow) {
+        // d/dx: lerp_z(lerp_y(b - a along x));  d/dy, d/dz alike
+        const float dxa = fmaf(ty, (a11 - a10) - (a01 - a00), a01 - a00), dxb = fmaf(ty, (b11 - b10) - (b01 - b00), b01 - b00);
+        const float ra0 = fmaf(tx, a01 - a00, a00), ra1 = fmaf(tx, a11 - a10, a10);
+        const float rb0 = fmaf(tx, b01 - b00, b00), rb1 = fmaf(tx, b11 - b10, b10);
+        const float dya = ra1 - ra0, dyb = rb1 - rb0;
+        gx = fmaf(go, IS3D ? fmaf(tz, dxb - dxa, dxa) : dxa, gx);
+        gy = fmaf(go, IS3D ? fmaf(tz, dyb - dya, dya) : dya, gy);
+        if (IS3D) gz = fmaf(go, fmaf(ty, rb1 - rb0, rb0) - fmaf(ty, ra1 - ra0, ra0), gz);
+      }
+      if (gsb) {
+        float* t = gsb + (size_t)c * sDHW;
+        const float wx0 = 1.f - tx, wy0 = 1.f - ty, wz0 = IS3D ? 1.f - tz : 1.f;
+        if (za && ya && xa) atomicAdd(t + zo0 + yo0 + xo0, go * wx0 * wy0 * wz0);
+        if (za && ya && xb) atomicAdd(t + zo0 + yo0 + xo1, go * tx * wy0 * wz0);
+        if (za && yb && xa) atomicAdd(t + zo0 + yo1 + xo0, go * wx0 * ty * wz0);
+        if (za && yb && xb) atomicAdd(t + zo0 + yo1 + xo1, go * tx * ty * wz0);
+        if (IS3D) {
+          if (zb && ya && xa) atomicAdd(t + zo1 + yo0 + xo0, go * wx0 * wy0 * tz);
+          if (zb && ya && xb) atomicAdd(t + zo1 + yo0 + xo1, go * tx * wy0 * tz);
+          if (zb && yb && xa) atomicAdd(t + zo1 + yo1 + xo0, go * wx0 * ty * tz);
+          if (zb && yb && xb) atomicAdd(t + zo1 + yo1 + xo1, go * tx * ty * tz);
+        }
+      }
+    }
+    if (gflow) {
+      float* gf = gflow + (size_t)b * g.nd * DHW + z * HW + y * g.W + x;
+      if (IS3D) { gf[0] = gz * g.rz; gf[DHW] = gy * g.ry; gf[2 * DHW] = gx * g.rx; }
+      else { gf[0] = gy * g.ry; gf[DHW] = gx * g.rx; }
+    }
+  }
+}
+
+static FastGeom make_fast_geom(int B, int C, int Ds, int Hs, int Ws, int D, int H, int W, int nd) {
+  FastGeom g;
+  g.D = D; g.H = H; g.W = W; g.Ds = Ds; g.Hs = Hs; g.Ws = Ws; g.B = B; g.C = C; g.nd = nd;
+  g.nzc = (D + ZU - 1) / ZU;
+  auto ratio = [](int s_src, int s) { return s > 1 ? (float)(s_src - 1) / (float)(s - 1) : 0.f; };
+  g.rz = nd == 3 ? ratio(Ds, D) : 0.f; g.ry = ratio(Hs, H); g.rx = ratio(Ws, W);
+  return g;
+}
+
 static int check_geom(int B, int C, int Ds, int Hs, int Ws, int D, int H, int W, int nd) {
   VXM_REQUIRE(nd == 2 || nd == 3, "warp: nd must be 2 or 3 (reference layers.py:41-46), got %d", nd);
   VXM_REQUIRE(B > 0 && C > 0 && Ds > 0 && Hs > 0 && Ws > 0 && D > 0 && H > 0 && W > 0, "warp: non-positive dimension");
@@ -166,9 +343,19 @@ extern "C" int vxm_warp_fwd(const float* src, const float* flow, float* out, int
   if (rc) return rc;
   VXM_REQUIRE(src && flow && out, "warp_fwd: null pointer");
   VXM_REQUIRE(mode == VXM_MODE_LINEAR || mode == VXM_MODE_NEAREST, "warp_fwd: bad mode %d", mode);
+  VXM_REQUIRE(arith == VXM_ARITH_TRUE_DIV || arith == VXM_ARITH_RECIPROCAL || (arith == VXM_ARITH_FAST && mode == VXM_MODE_LINEAR),
+              "warp_fwd: bad arith %d (VXM_ARITH_FAST is for the linear mode only)", arith);
+  cudaStream_t st = as_stream(stream);
+  if (arith == VXM_ARITH_FAST) {
+    FastGeom fg = make_fast_geom(B, C, Ds, Hs, Ws, D, H, W, nd);
+    VXM_REQUIRE((size_t)fg.nzc * B <= 65535u, "warp: D*B exceeds the launch grid limit");
+    dim3 block(TX, TY, 1), grid((W + TX - 1) / TX, (H + TY - 1) / TY, fg.nzc * B);
+    if (nd == 3) warp_fwd_fast_kernel<true><<<grid, block, 0, st>>>(src, flow, out, fg);
+    else warp_fwd_fast_kernel<false><<<grid, block, 0, st>>>(src, flow, out, fg);
+    return check_launch("warp_fwd");
+  }
   WarpGeom g = make_geom(B, C, Ds, Hs, Ws, D, H, W, nd);
   dim3 block(TX, TY, 1), grid((W + TX - 1) / TX, (H + TY - 1) / TY, D * B);
-  cudaStream_t st = as_stream(stream);
   WARP_DISPATCH(warp_fwd_kernel, src, flow, out, g);
   return check_launch("warp_fwd");
 }
@@ -179,6 +366,16 @@ extern "C" int vxm_warp_bwd(const float* grad_out, const float* src, const float
   int rc = check_geom(B, C, Ds, Hs, Ws, D, H, W, nd);
   if (rc) return rc;
   VXM_REQUIRE(grad_out && src && flow, "warp_bwd: null pointer");
+  VXM_REQUIRE(arith == VXM_ARITH_TRUE_DIV || arith == VXM_ARITH_RECIPROCAL || (arith == VXM_ARITH_FAST && mode == VXM_MODE_LINEAR),
+              "warp_bwd: bad arith %d (VXM_ARITH_FAST is for the linear mode only)", arith);
+  if (arith == VXM_ARITH_FAST) {
+    FastGeom fg = make_fast_geom(B, C, Ds, Hs, Ws, D, H, W, nd);
+    dim3 block(TX, TY, 1), grid((W + TX - 1) / TX, (H + TY - 1) / TY, fg.nzc * B);
+    cudaStream_t st = as_stream(stream);
+    if (nd == 3) warp_bwd_fast_kernel<true><<<grid, block, 0, st>>>(grad_out, src, flow, grad_src, grad_flow, fg);
+    else warp_bwd_fast_kernel<false><<<grid, block, 0, st>>>(grad_out, src, flow, grad_src, grad_flow, fg);
+    return check_launch("warp_bwd");
+  }
   WarpGeom g = make_geom(B, C, Ds, Hs, Ws, D, H, W, nd);
   // d coord / d flow = ((Ssrc-1)/2) * 2 / (Sflow-1)   (GridSampler.h:45-47 and layers.py:37)
   float mx = (g.ax.src_sm1 * 0.5f) * 2.0f / g.ax.sm1;

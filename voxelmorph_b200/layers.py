@@ -14,7 +14,7 @@ import torch.nn as nn
 from . import _lib
 
 MODE_LINEAR, MODE_NEAREST = 0, 1
-ARITH_TRUE_DIV, ARITH_RECIPROCAL = 0, 1
+ARITH_TRUE_DIV, ARITH_RECIPROCAL, ARITH_FAST = 0, 1, 2
 
 
 def default_arith():
@@ -22,6 +22,15 @@ def default_arith():
     true division — the oracle this repo is bit-exact against; 'cuda' replays torch's CUDA
     multiply-by-reciprocal."""
     return ARITH_RECIPROCAL if os.environ.get("VXM_B200_NEAREST_ARITH", "cpu") == "cuda" else ARITH_TRUE_DIV
+
+
+def linear_arith():
+    """Coordinate arithmetic of the LINEAR resampler (SpatialTransformer 'bilinear', VecInt).  Default 'fast':
+    coord = (p + flow) * (Ssrc-1)/(S-1) — the reference's map without its fp32 normalise / un-normalise round trip;
+    agrees with the replayed arithmetic to a few 1e-6 of the value range (north_star asks 1e-4) and lets the kernels run
+    memory bound.  VXM_B200_LINEAR_ARITH=exact replays torch's arithmetic op for op (bit-identical to the torch CPU
+    reference on every input tried), like the nearest mode always does."""
+    return default_arith() if os.environ.get("VXM_B200_LINEAR_ARITH", "fast") == "exact" else ARITH_FAST
 
 
 def _dims(t):
@@ -96,7 +105,7 @@ class SpatialTransformer(nn.Module):
             # F.grid_sample raises for anything but bilinear / nearest / bicubic; bicubic is 4-D only
             raise ValueError("nn.functional.grid_sample(): expected mode to be 'bilinear' or 'nearest', "
                              "but got: '%s'" % self.mode)
-        return _WarpFn.apply(src, flow, m, default_arith())
+        return _WarpFn.apply(src, flow, m, linear_arith() if m == MODE_LINEAR else default_arith())
 
 
 class _VecIntFn(torch.autograd.Function):
@@ -110,9 +119,16 @@ class _VecIntFn(torch.autograd.Function):
         lib = _lib.load()
         out = torch.empty_like(vec)
         need_grad = ctx.needs_input_grad[0]
+        if arith == ARITH_FAST and (nd != 3 or nsteps < 1 or min(D, H, W) < 2):
+            arith = default_arith()      # the float4 fast path is 3-D only
         states = work = None
         if nsteps > 0:
-            if need_grad:
+            if arith == ARITH_FAST:
+                if need_grad:
+                    states = torch.empty(int(lib.vxm_vecint_fast_states_bytes(B, D, H, W, nsteps)), dtype=torch.uint8, device=vec.device)
+                else:
+                    work = torch.empty(int(lib.vxm_vecint_fast_work_bytes(B, D, H, W, 0)), dtype=torch.uint8, device=vec.device)
+            elif need_grad:
                 states = torch.empty((nsteps,) + tuple(vec.shape), dtype=torch.float32, device=vec.device)
             else:
                 work = torch.empty_like(vec)
@@ -127,8 +143,13 @@ class _VecIntFn(torch.autograd.Function):
         nsteps, arith, (B, D, H, W, nd) = ctx.cfg
         gout = _lib.contig(gout)
         gvel = torch.empty_like(gout)
-        work = torch.empty((2,) + tuple(gout.shape), dtype=torch.float32, device=gout.device) if nsteps > 0 else None
         lib = _lib.load()
+        work = None
+        if nsteps > 0:
+            if arith == ARITH_FAST:
+                work = torch.empty(int(lib.vxm_vecint_fast_work_bytes(B, D, H, W, 1)), dtype=torch.uint8, device=gout.device)
+            else:
+                work = torch.empty((2,) + tuple(gout.shape), dtype=torch.float32, device=gout.device)
         _lib.check(lib.vxm_vecint_bwd(_lib.ptr(gout), _lib.ptr(ctx.states), _lib.ptr(gvel), _lib.ptr(work), B, D, H, W,
                                       nd, nsteps, arith, _lib.stream_ptr()), "vxm_vecint_bwd")
         return gvel, None, None
@@ -146,7 +167,7 @@ class VecInt(nn.Module):
         self.transformer = SpatialTransformer(inshape)
 
     def forward(self, vec):
-        return _VecIntFn.apply(vec, self.nsteps, default_arith())
+        return _VecIntFn.apply(vec, self.nsteps, linear_arith())
 
 
 class _ResizeFn(torch.autograd.Function):

@@ -163,6 +163,16 @@ def _use_s(ca, cb, cout):
     return _variant() in ("auto", "s") and bool(_lib.load().vxm_conv3d_tcs_supported(ca, cb, cout))
 
 
+def _use_s2(xa, xb, coutp, full, up, kd):
+    """VXM_B200_TCS2=1: the two-issuer variant wherever the one-issuer kernel would pick 8-row tiles."""
+    import os
+    if os.environ.get("VXM_B200_TCS2", "0") != "1":
+        return False
+    cin = (0 if xa is None else xa.shape[-1]) + (0 if xb is None else xb.shape[-1])
+    H = full.shape[2] * (2 if (xb is None and up) else 1)
+    return coutp in (16, 32) and cin in (8, 16, 32, 48) and H > 4 and not (cin == 48 and coutp == 32)
+
+
 def pack_weights_t(w, transposed=False, variant=None):
     """Packed weights for a kw-stacked kernel.  Returns (tensor, (coutp, variant))."""
     lib = _lib.load()
@@ -188,6 +198,8 @@ def conv_fwd_t(xa, xb, wpk, coutp, bias, cout, kd, up=False, out_fp32_planar=Fal
     coutp, variant = coutp if isinstance(coutp, tuple) else (coutp, "t")
     fwd = lib.vxm_conv3d_tcs_fwd if variant == "s" else lib.vxm_conv3d_tct_fwd
     full = xb if xb is not None else xa
+    if variant == "s" and _use_s2(xa, xb, coutp, full, up, kd):
+        fwd = lib.vxm_conv3d_tcs2_fwd
     B, D, H, W = full.shape[0], full.shape[1], full.shape[2], full.shape[3]
     if xb is None and up:
         D, H, W = (D * 2 if kd == 3 else D), H * 2, W * 2
