@@ -188,6 +188,17 @@ int vxm_conv3d_tcs_fwd(const void* xa, const void* xb, const void* wpk, const fl
 int vxm_conv3d_tcs2_fwd(const void* xa, const void* xb, const void* wpk, const float* bias, void* out, const void* mask,
                        int B, int D, int H, int W, int Ca, int Cb, int up, int Cout, int coutp, int kd, int out_mode,
                        float slope, void* out2, int csplit, void* stream);
+/* Split-precision ("bf16x3") passes of the same kernel — the in-tolerance tensor-core mode (reference layer:
+ * voxelmorph/torch/networks.py:290-305 in fp32).  Every operand is a bf16 pair hi + lo (16 mantissa bits); a layer is
+ * three launches that accumulate  x_lo*w_hi + x_hi*w_lo + x_hi*w_hi  in fp32:
+ *   out_mode 2: out (fp32, channels-last, `coutp` channels per voxel) = acc_in + conv   (no bias / activation; acc_in may
+ *               be NULL or alias out);
+ *   out_mode 3: x = act(acc_in + conv + bias) stored as the bf16 pair out (hi), out_lo (lo = bf16(x - hi));
+ *   out_mode 1: fp32 planar out = acc_in + conv + bias (the flow head).
+ * acc_in has `coutp` channels per voxel. */
+int vxm_conv3d_tcs_fwd_acc(const void* xa, const void* xb, const void* wpk, const float* bias, void* out, void* out_lo,
+                           const float* acc_in, int B, int D, int H, int W, int Ca, int Cb, int up, int Cout, int coutp,
+                           int kd, int out_mode, float slope, void* stream);
 /* Weight (and bias) gradient on tensor cores.  x sources as in vxm_conv3d_tc_fwd (the layer's forward input);
  * gz = gradient w.r.t. the convolution output (already multiplied by the activation derivative): bf16 NDHWC with
  * Cg in {8,16,32} channels, or nplanar_g (<= 4) planar fp32 volumes (flow head).  grad_w: fp32
@@ -213,6 +224,12 @@ int vxm_unpool_combine_ndhwc_bf16(const void* e_fine, const void* g_skip_fine, c
  * channels are zero.  Feeds the fp32 images / the fp32 flow gradient to the tensor-core kernels. */
 int vxm_planar_to_ndhwc8_bf16(const float* const* planes, const long long* bstrides, int nplanes, void* out, int B,
                               size_t V, void* stream);
+/* split-precision variants: out_hi = bf16(x), out_lo = bf16(x - out_hi); MaxPool(2) of a (hi, lo) pair tensor (the
+ * maximum is taken on hi + lo, the winning child's pair is copied) */
+int vxm_planar_to_ndhwc8_split_bf16(const float* const* planes, const long long* bstrides, int nplanes, void* out_hi,
+                                    void* out_lo, int B, size_t V, void* stream);
+int vxm_pool2_split_ndhwc_bf16(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, int B, int Dc, int Hc, int Wc,
+                               int C, int nd, void* stream);
 /* out[c] = sum_{b,v} x[b][c][v] for planar fp32 x (B,C,V), C <= 32; work: 128*C floats */
 int vxm_planar_channel_sums(const float* x, float* out, void* work, int B, int C, size_t V, void* stream);
 

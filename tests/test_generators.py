@@ -47,6 +47,8 @@ CASES = {
     "s2s_nowarp": dict(kind="scan_to_scan", kw=dict(batch_size=1, no_warp=True)),
     "s2a": dict(kind="scan_to_atlas", kw=dict(batch_size=2)),
     "s2a_bidir_seg": dict(kind="scan_to_atlas", kw=dict(batch_size=1, bidir=True, segs=True)),
+    "semi": dict(kind="semisupervised", kw=dict(labels=[1, 2, 3], downsize=2)),
+    "semi_atlas": dict(kind="semisupervised", kw=dict(labels=[0, 2], downsize=2, atlas=True)),
 }
 
 
@@ -57,6 +59,9 @@ def run_case(mod, files, case, steps=6, seed=7):
         gen = mod.volgen(files, **kw)
     elif case["kind"] == "scan_to_scan":
         gen = mod.scan_to_scan(files, **kw)
+    elif case["kind"] == "semisupervised":   # the npz files carry 'vol' and 'seg' (seg_names=True, generators.py:158)
+        atlas = files[0] if kw.pop("atlas", False) else None
+        gen = mod.semisupervised(files, True, kw.pop("labels"), atlas_file=atlas, **kw)
     else:
         atlas = np.load(files[0])["vol"][np.newaxis, ..., np.newaxis]
         gen = mod.scan_to_atlas(files, atlas, **kw)

@@ -24,6 +24,10 @@ struct ConvSArgs {
   const __nv_bfloat16* wpk; const float* bias;
   void* out; const __nv_bfloat16* mask;
   void* out2; int csplit;   // optional second bf16 output: channels [csplit, Cout) (single-pass dgrad of a concat layer)
+  // split-precision (bf16x3) passes: `acc_in` (fp32 channels-last, COUT channels per voxel) is added to the tile before the
+  // epilogue; out_mode 2 stores the raw fp32 sums back in that layout (no bias / activation), out_mode 3 applies bias +
+  // activation and stores the result as a bf16 (hi, lo) pair: hi -> out, lo = bf16(x - hi) -> out_lo
+  const float* acc_in; void* out_lo;
   int B, D, H, W, Ca, Cb, up, upd, Cout, out_mode;
   float slope;
   int tiles_h, tiles_w, dchunk, nchunks, nitems, nslot;
@@ -269,6 +273,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const ConvSArgs a
 #pragma unroll
         for (int c0 = 0; c0 < COUT; c0 += 16) {
           uint32_t r0[16], r1[16], r2[16];
+          float4 ain[4];
+          if (a.acc_in && valid) {      // partial sums of the earlier split-precision passes (issued before the TMEM wait)
+            const float4* ap = reinterpret_cast<const float4*>(a.acc_in + vox * COUT + c0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ain[q] = __ldg(ap + q);
+          }
           tmem_ld16(taddr + c0, r0);
           tmem_ld16(taddr + COUT + c0, r1);
           tmem_ld16(taddr + 2 * COUT + c0, r2);
@@ -284,7 +294,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const ConvSArgs a
             const float p2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[c]), 1);
             v[c] = (p0 + __uint_as_float(r1[c])) + p2;      // out[w'] = P0[w'-1] + P1[w'] + P2[w'+1]
           }
-          if (valid && c0 < a.Cout) {
+          if (a.acc_in && valid) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { v[4 * q] += ain[q].x; v[4 * q + 1] += ain[q].y; v[4 * q + 2] += ain[q].z; v[4 * q + 3] += ain[q].w; }
+          }
+          if (a.out_mode == 2) {
+            if (valid) {
+              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + vox * COUT + c0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+          } else if (a.out_mode == 3) {
+            if (valid && c0 < a.Cout) {
+#pragma unroll
+              for (int q = 0; q < 16; q += 8) {
+                if (c0 + q < a.Cout) {
+                  uint32_t hi[4], lo[4];
+#pragma unroll
+                  for (int e = 0; e < 8; e += 2) {
+                    float x0 = v[q + e] + bias_at(c0 + q + e), x1 = v[q + e + 1] + bias_at(c0 + q + e + 1);
+                    if (a.slope >= 0.f) { x0 = x0 >= 0.f ? x0 : x0 * a.slope; x1 = x1 >= 0.f ? x1 : x1 * a.slope; }
+                    const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                    hi[e >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                    lo[e >> 1] = pack_bf16x2(x0 - __bfloat162float(h0), x1 - __bfloat162float(h1));
+                  }
+                  const size_t o = vox * a.Cout + c0 + q;
+                  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out_lo) + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+              }
+            }
+          } else if (valid && c0 < a.Cout) {
             if (a.out_mode == 0) {
 #pragma unroll
               for (int q = 0; q < 16; q += 8) {
@@ -397,14 +437,35 @@ extern "C" int vxm_conv3d_tcs_supported(int Ca, int Cb, int Cout) {
   return (Cout <= 64) && (cin == 8 || cin == 16 || cin == 32 || cin == 48 || cin == 64) && Ca % 8 == 0 && Cb % 8 == 0 && split_ok;
 }
 
+static int conv_tcs_launch(const void* xa, const void* xb, const void* wpk, const float* bias, void* out, const void* mask,
+                           int B, int D, int H, int W, int Ca, int Cb, int up, int Cout, int coutp, int kd, int out_mode,
+                           float slope, void* out2, int csplit, const float* acc_in, void* out_lo, void* stream);
+
 extern "C" int vxm_conv3d_tcs_fwd(const void* xa, const void* xb, const void* wpk, const float* bias, void* out, const void* mask,
                                   int B, int D, int H, int W, int Ca, int Cb, int up, int Cout, int coutp, int kd, int out_mode,
                                   float slope, void* out2, int csplit, void* stream) {
+  VXM_REQUIRE(out_mode == 0 || out_mode == 1, "conv3d_tcs_fwd: out_mode must be 0 (bf16 channels-last) or 1 (fp32 planar)");
+  return conv_tcs_launch(xa, xb, wpk, bias, out, mask, B, D, H, W, Ca, Cb, up, Cout, coutp, kd, out_mode, slope, out2, csplit,
+                         nullptr, nullptr, stream);
+}
+
+extern "C" int vxm_conv3d_tcs_fwd_acc(const void* xa, const void* xb, const void* wpk, const float* bias, void* out, void* out_lo,
+                                      const float* acc_in, int B, int D, int H, int W, int Ca, int Cb, int up, int Cout, int coutp,
+                                      int kd, int out_mode, float slope, void* stream) {
+  VXM_REQUIRE(out_mode >= 1 && out_mode <= 3, "conv3d_tcs_fwd_acc: out_mode must be 1 (fp32 planar), 2 (fp32 partial sums) or 3 (bf16 hi/lo pair)");
+  VXM_REQUIRE(out_mode != 3 || out_lo, "conv3d_tcs_fwd_acc: out_mode 3 needs out_lo");
+  return conv_tcs_launch(xa, xb, wpk, bias, out, nullptr, B, D, H, W, Ca, Cb, up, Cout, coutp, kd, out_mode, slope, nullptr, 0,
+                         acc_in, out_lo, stream);
+}
+
+static int conv_tcs_launch(const void* xa, const void* xb, const void* wpk, const float* bias, void* out, const void* mask,
+                           int B, int D, int H, int W, int Ca, int Cb, int up, int Cout, int coutp, int kd, int out_mode,
+                           float slope, void* out2, int csplit, const float* acc_in, void* out_lo, void* stream) {
   VXM_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && wpk && out, "conv3d_tcs_fwd: bad argument");
   VXM_REQUIRE(kd == 1 || kd == 3, "conv3d_tcs_fwd: kd must be 1 or 3");
   VXM_REQUIRE(coutp == 16 || coutp == 32 || coutp == 48 || coutp == 64, "conv3d_tcs_fwd: padded Cout must be 16, 32, 48 or 64");
   VXM_REQUIRE(!out2 || (out_mode == 0 && csplit > 0 && csplit < Cout && csplit % 8 == 0 && !mask), "conv3d_tcs_fwd: bad output split");
-  VXM_REQUIRE(Cout > 0 && Cout <= coutp && (out_mode == 1 || Cout % 8 == 0), "conv3d_tcs_fwd: unsupported Cout %d", Cout);
+  VXM_REQUIRE(Cout > 0 && Cout <= coutp && (out_mode == 1 || out_mode == 2 || Cout % 8 == 0), "conv3d_tcs_fwd: unsupported Cout %d", Cout);
   VXM_REQUIRE(vxm_conv3d_tcs_supported(Ca, Cb, Cout), "conv3d_tcs_fwd: channel counts (%d,%d)->%d unsupported", Ca, Cb, Cout);
   VXM_REQUIRE((Ca == 0 || xa) && (Cb == 0 || xb), "conv3d_tcs_fwd: missing source tensor");
   VXM_REQUIRE(!up || (H % 2 == 0 && W % 2 == 0 && (kd == 1 || D % 2 == 0)), "conv3d_tcs_fwd: upsampled source needs even sizes");
@@ -414,6 +475,7 @@ extern "C" int vxm_conv3d_tcs_fwd(const void* xa, const void* xb, const void* wp
   groups_of(cin, &g0, &g1);
   a.xa = (const __nv_bfloat16*)xa; a.xb = (const __nv_bfloat16*)xb; a.wpk = (const __nv_bfloat16*)wpk; a.bias = bias;
   a.out = out; a.mask = (const __nv_bfloat16*)mask; a.out2 = out2; a.csplit = csplit;
+  a.acc_in = acc_in; a.out_lo = out_lo;
   a.B = B; a.D = D; a.H = H; a.W = W; a.Ca = Ca; a.Cb = Cb; a.up = up; a.upd = (up && kd == 3) ? 1 : 0;
   a.Cout = Cout; a.out_mode = out_mode; a.slope = slope;
   a.wbytes = (uint32_t)vxm_conv3d_tcs_packed_bytes(cin, coutp, kd);

@@ -182,6 +182,51 @@ __global__ void __launch_bounds__(256) planar_to_ndhwc8_kernel(PlanarSrc src, __
   }
 }
 
+// split-precision (bf16x3) variants: a value is carried as a bf16 pair hi = bf16(x), lo = bf16(x - hi)  (16 mantissa bits)
+__global__ void __launch_bounds__(256) planar_to_ndhwc8_split_kernel(PlanarSrc src, __nv_bfloat16* __restrict__ out_hi,
+                                                                     __nv_bfloat16* __restrict__ out_lo, int B, size_t V) {
+  size_t n = (size_t)B * V;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    size_t b = i / V, v = i - b * V;
+    V8 h, l;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float x = c < src.n ? __ldg(src.p[c] + b * src.bstride[c] + v) : 0.f;
+      h.v[c] = __bfloat162float(__float2bfloat16_rn(x));
+      l.v[c] = x - h.v[c];
+    }
+    st8(out_hi + i * 8, h);
+    st8(out_lo + i * 8, l);
+  }
+}
+
+// MaxPool(2) of a (hi, lo) pair tensor: the maximum is taken on hi + lo, the winning child's pair is copied (first
+// maximal child wins ties, like ATen)
+__global__ void __launch_bounds__(256) pool_split_ndhwc_kernel(const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16* __restrict__ xl,
+                                                               __nv_bfloat16* __restrict__ yh, __nv_bfloat16* __restrict__ yl, PoolGeom g) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int b, d, h, w, c8;
+  if (!decode(g, i, b, d, h, w, c8)) return;
+  const int C = g.C8 * 8;
+  V8 m, mh, ml;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { m.v[e] = -INFINITY; mh.v[e] = -INFINITY; ml.v[e] = 0.f; }
+  for (int kd = 0; kd < g.fd; ++kd)
+    for (int kh = 0; kh < 2; ++kh)
+      for (int kw = 0; kw < 2; ++kw) {
+        const size_t o = fine_index(g, b, d, h, w, kd, kh, kw) * C + c8 * 8;
+        V8 th = ld8(xh + o), tl = ld8(xl + o);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float t = th.v[e] + tl.v[e];
+          if (t > m.v[e] || t != t) { m.v[e] = t; mh.v[e] = th.v[e]; ml.v[e] = tl.v[e]; }
+        }
+      }
+  const size_t o = ((((size_t)b * g.Dc + d) * g.Hc + h) * g.Wc + w) * C + c8 * 8;
+  st8(yh + o, mh);
+  st8(yl + o, ml);
+}
+
 static int make_pool_geom(int B, int Dc, int Hc, int Wc, int C, int nd, PoolGeom* g) {
   VXM_REQUIRE(B > 0 && Dc > 0 && Hc > 0 && Wc > 0 && C > 0 && C % 8 == 0, "ndhwc op: bad dimensions (C must be a multiple of 8)");
   VXM_REQUIRE(nd == 2 || nd == 3, "ndhwc op: nd must be 2 or 3");
@@ -250,4 +295,29 @@ extern "C" int vxm_planar_to_ndhwc8_bf16(const float* const* planes, const long 
   size_t cap = (size_t)sm_count() * 16;
   planar_to_ndhwc8_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, as_stream(stream)>>>(src, (__nv_bfloat16*)out, B, V);
   return check_launch("planar_to_ndhwc8");
+}
+
+extern "C" int vxm_planar_to_ndhwc8_split_bf16(const float* const* planes, const long long* bstrides, int nplanes, void* out_hi,
+                                               void* out_lo, int B, size_t V, void* stream) {
+  VXM_REQUIRE(planes && bstrides && out_hi && out_lo && nplanes > 0 && nplanes <= 8 && B > 0 && V > 0, "planar_to_ndhwc8_split: bad argument");
+  PlanarSrc src{};
+  src.n = nplanes;
+  for (int i = 0; i < nplanes; ++i) { src.p[i] = planes[i]; src.bstride[i] = bstrides[i]; }
+  size_t n = (size_t)B * V;
+  size_t blocks = (n + 255) / 256;
+  size_t cap = (size_t)sm_count() * 16;
+  planar_to_ndhwc8_split_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, as_stream(stream)>>>(
+      src, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, B, V);
+  return check_launch("planar_to_ndhwc8_split");
+}
+
+extern "C" int vxm_pool2_split_ndhwc_bf16(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, int B, int Dc, int Hc, int Wc,
+                                          int C, int nd, void* stream) {
+  PoolGeom g;
+  int rc = make_pool_geom(B, Dc, Hc, Wc, C, nd, &g);
+  if (rc) return rc;
+  VXM_REQUIRE(x_hi && x_lo && y_hi && y_lo, "pool2_split_ndhwc: null pointer");
+  pool_split_ndhwc_kernel<<<pool_grid(g), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo,
+                                                                       (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo, g);
+  return check_launch("pool2_split_ndhwc");
 }

@@ -41,6 +41,28 @@ class _PackCache:
 _cache = _PackCache()
 
 
+def supports(model):
+    """True when every convolution of `model` (a VxmDense) has a shape the tensor-core kernels implement: feature
+    counts in {8, 16, 32}, concatenated inputs a multiple of 16 and at most 64 channels, at most 8 image planes."""
+    try:
+        unet = model.unet_model
+        convs = [b.main for lvl in unet.encoder for b in lvl] + [b.main for lvl in unet.decoder for b in lvl] + \
+                [b.main for b in unet.remaining]
+        first = convs[0]
+        if first.weight.shape[1] > 8 or first.weight.dim() not in (4, 5):
+            return False
+        for i, c in enumerate(convs):
+            co, ci = c.weight.shape[0], c.weight.shape[1]
+            if co not in (8, 16, 32):
+                return False
+            if i > 0 and (ci % 16 or ci > 64):
+                return False
+        fl = model.flow
+        return fl.weight.shape[1] % 16 == 0 and fl.weight.shape[1] <= 64 and fl.weight.shape[0] <= 8
+    except AttributeError:
+        return False
+
+
 def _check_cout(c, what):
     if c not in (8, 16, 32):
         raise _lib.VxmError("bf16 tensor-core engine: %s has %d channels; supported feature counts are 8, 16 and 32 "
@@ -79,7 +101,21 @@ def _unpool_combine(e_fine, g_skip, g_pool, nd, slope):
 
 class _Conv:
     """One convolution of the tape: inputs, output, parameters."""
-    __slots__ = ("w", "b", "planar", "xa", "xb", "up", "out", "slope", "cin", "cout", "a_id", "b_id", "out_id", "planar_out")
+    __slots__ = ("w", "b", "planar", "xa", "xb", "up", "out", "slope", "cin", "cout", "a_id", "b_id", "out_id", "planar_out",
+                 "xa_lo", "xb_lo")
+
+
+def _run_conv_split(cv, kd):
+    """Forward of one tape entry in split precision (three tensor-core passes, see tc.conv_fwd_split).  Returns the
+    (hi, lo) output pair, or the fp32 planar flow."""
+    def packs():
+        wh, wl = tc.split_weights(cv.w)
+        return tc.pack_weights_t(wh, variant="s"), tc.pack_weights_t(wl, variant="s")
+    pk = _cache.get(cv.w, "fwd_split", packs)
+    xa = None if cv.xa is None else (cv.xa, cv.xa_lo)
+    xb = None if cv.xb is None else (cv.xb, cv.xb_lo)
+    return tc.conv_fwd_split(xa, xb, pk, cv.b.detach() if cv.b is not None else None, cv.cout, kd, up=cv.up,
+                             out_fp32_planar=cv.planar_out, slope=cv.slope)
 
 
 def _run_conv(cv, kd):
@@ -95,8 +131,10 @@ def _run_conv(cv, kd):
                        out_fp32_planar=cv.planar_out, slope=cv.slope)
 
 
-def forward_tape(model, source, target):
-    """Runs Unet + flow head, returns (flow fp32 (B,nd,*vol), tape)."""
+def forward_tape(model, source, target, split=False):
+    """Runs Unet + flow head, returns (flow fp32 (B,nd,*vol), tape).  `split`: split-precision (bf16x3) forward — every
+    activation is a (hi, lo) bf16 pair and every layer three tensor-core passes; the tape keeps the hi parts, which is
+    what the (bf16-operand) backward reads."""
     unet = model.unet_model
     nd = source.dim() - 2
     kd = 3 if nd == 3 else 1
@@ -107,6 +145,7 @@ def forward_tape(model, source, target):
         raise _lib.VxmError("bf16 engine: at most 8 input feature planes (src_feats + trg_feats)")
     tape = []            # list of ("conv", _Conv) / ("pool", in_id, out_id)
     tensors = {}         # id -> bf16 NDHWC tensor
+    lows = {}            # id -> lo part (split precision only)
     producer = {}        # id -> "conv" | "pool"
     next_id = [0]
 
@@ -123,6 +162,8 @@ def forward_tape(model, source, target):
         cv.up, cv.slope, cv.planar_out = up, slope, planar_out
         cv.cout, cv.cin = cv.w.shape[0], cv.w.shape[1]
         cv.a_id, cv.b_id = a_id, b_id
+        cv.xa_lo = lows.get(a_id) if split else None
+        cv.xb_lo = lows.get(b_id) if split else None
         if not planar_out:
             _check_cout(cv.cout, "a U-Net convolution output")
         if planar is None:
@@ -135,9 +176,12 @@ def forward_tape(model, source, target):
             elif ca + cb != cv.cin or (ca + cb) % 16 or ca + cb > 64:
                 raise _lib.VxmError("bf16 engine: unsupported convolution input channels %d (+%d); need a multiple of 16, at most 64"
                                     % (ca, cb))
-        out = _run_conv(cv, kd)
-        cv.out = out
+        out = _run_conv_split(cv, kd) if split else _run_conv(cv, kd)
         cv.out_id = new_id()
+        if split and not planar_out:
+            out, lows[cv.out_id] = out
+        cv.out = out
+        cv.xa_lo = cv.xb_lo = None      # the backward reads the hi parts only
         if not planar_out:
             tensors[cv.out_id] = out
             producer[cv.out_id] = "conv"
@@ -145,8 +189,14 @@ def forward_tape(model, source, target):
         return cv.out_id
 
     def pool(in_id):
-        y = _pool(tensors[in_id], nd)
         oid = new_id()
+        if split:
+            y, lows[oid] = tc.pool_split((tensors[in_id], lows[in_id]), nd)
+        else:
+            y = _pool(tensors[in_id], nd)
+        return _pool_done(y, in_id, oid)
+
+    def _pool_done(y, in_id, oid):
         tensors[oid] = y
         producer[oid] = "pool"
         tape.append(("pool", in_id, oid))
@@ -154,7 +204,10 @@ def forward_tape(model, source, target):
 
     # the fp32 images enter as one bf16 channels-last tensor with 8 channels (src planes, trg planes, zeros)
     cur = new_id()
-    tensors[cur] = tc.planar_to_ndhwc8(planes)
+    if split:
+        tensors[cur], lows[cur] = tc.planar_to_ndhwc8_split(planes)
+    else:
+        tensors[cur] = tc.planar_to_ndhwc8(planes)
     producer[cur] = "input"
     skips = [None]
     for level, convs in enumerate(unet.encoder):
@@ -272,19 +325,26 @@ def _slope_of(ctx, tid):
 
 class _UnetFlowFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model, source, target, *params):
-        flow, tape = forward_tape(model, source, target)
+    def forward(ctx, model, source, target, split, *params):
+        flow, tape = forward_tape(model, source, target, split=split)
         ctx.tape = tape
         ctx.params = params
+        ctx.model_ref = model
         return flow
 
     @staticmethod
     def backward(ctx, g_flow):
+        dp = getattr(ctx.model_ref, "_dp", None)
+        if dp is not None:
+            dp.schedule()      # gradients written straight into .grad views bypass the parameter hooks
         grads = backward_tape(ctx.tape, g_flow)
         ctx.tape = None
-        return (None, None, None) + tuple(grads.get(p) for p in ctx.params)
+        return (None, None, None, None) + tuple(grads.get(p) for p in ctx.params)
 
 
-def unet_flow(model, source, target):
+def unet_flow(model, source, target, split=False):
+    """flow = model.flow(model.unet_model(cat(source, target))) on the tensor-core engine.  split=False: bf16 operands
+    (throughput mode); split=True: bf16x3 split precision in the forward (flow within 1e-4 of the fp32 reference), the
+    backward uses bf16 operands in both modes."""
     params = [p for p in list(model.unet_model.parameters()) + list(model.flow.parameters())]
-    return _UnetFlowFn.apply(model, source, target, *params)
+    return _UnetFlowFn.apply(model, source, target, bool(split), *params)

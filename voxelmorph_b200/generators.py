@@ -25,7 +25,7 @@ from collections import OrderedDict
 
 import numpy as np
 
-__all__ = ["VolumeCache", "load_volfile", "volgen", "scan_to_scan", "scan_to_atlas", "Prefetcher"]
+__all__ = ["VolumeCache", "load_volfile", "volgen", "scan_to_scan", "scan_to_atlas", "semisupervised", "Prefetcher"]
 
 
 def _pinned_empty(shape, dtype):
@@ -101,8 +101,17 @@ class VolumeCache:
         self.hits = self.misses = 0
 
     def get(self, src, np_var="vol", pad_shape=None, resize_factor=1, add_feat_axis=True):
-        key = (src if isinstance(src, (str, os.PathLike)) else ("array", id(src)), np_var,
-               None if pad_shape is None else tuple(pad_shape), resize_factor, bool(add_feat_axis))
+        if not isinstance(src, (str, os.PathLike)):
+            # preloaded arrays are never cached (an id()-keyed entry could outlive its array and be served to a later
+            # array that reuses the address, or go stale when the array is modified in place): like the reference
+            # (py/utils.py:95-99) they are passed through, with the same padding / axis handling
+            vol = np.asarray(src)
+            if pad_shape:
+                vol = _pad_centered(vol, pad_shape)
+            if add_feat_axis:
+                vol = vol[..., np.newaxis]
+            return _resize_nearest(vol, resize_factor)
+        key = (os.fspath(src), np_var, None if pad_shape is None else tuple(pad_shape), resize_factor, bool(add_feat_axis))
         with self._lock:
             hit = self._items.get(key)
             if hit is not None:
@@ -140,7 +149,20 @@ class VolumeCache:
         return len(self._items)
 
 
-_default_cache = VolumeCache()
+def _default_cache_bytes():
+    """Bound of the process-wide cache: VXM_B200_CACHE_GB, else a quarter of the host's RAM, at most 16 GiB
+    (page-locking more than that can destabilise the host)."""
+    env = os.environ.get("VXM_B200_CACHE_GB")
+    if env:
+        return int(float(env) * (1 << 30))
+    try:
+        ram = os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES")
+    except (ValueError, OSError, AttributeError):
+        ram = 32 << 30
+    return int(min(16 << 30, ram // 4))
+
+
+_default_cache = VolumeCache(max_bytes=_default_cache_bytes())
 
 
 def load_volfile(filename, np_var="vol", add_batch_axis=False, add_feat_axis=False, pad_shape=None, resize_factor=1, cache=None):
@@ -243,6 +265,39 @@ def scan_to_atlas(vol_names, atlas, bidir=False, batch_size=1, no_warp=False, se
         if not no_warp:
             outvols.append(zeros)
         yield (invols, outvols)
+
+
+def semisupervised(vol_names, seg_names, labels, atlas_file=None, downsize=2, prob_dtype=np.float32, zeros_dtype=np.float32, cache=None):
+    """Semi-supervised pairs ("next" row N2; reference generators.py:146-194): yields
+    ([src_vol, trg_vol, src_prob_seg], [trg_vol, zeros, trg_prob_seg]) with the label maps turned into one-hot
+    probability maps over `labels` and sub-sampled by `downsize` per axis.  Batch size is 1, 3-D only, like the
+    reference; the draws from np.random follow its order (one volgen draw for the source, one for the target unless an
+    atlas file supplies it).  The one-hot is built on the sub-sampled label map in one comparison against the label
+    vector (float32 instead of float64: a 30-label map at 80x96x112 is 103 MB rather than 206 MB per segmentation)."""
+    labels = np.asarray(labels)
+    cache = _default_cache if cache is None else cache
+    gen = volgen(vol_names, segs=seg_names, np_var="vol", cache=cache)
+
+    def prob_seg(seg):
+        if seg.shape[0] != 1 or seg.ndim != 5:
+            raise ValueError("semisupervised: segmentations must be (1, D, H, W, 1) label maps (batch size 1, 3-D)")
+        sub = seg[0, ::downsize, ::downsize, ::downsize, 0]
+        return (sub[..., np.newaxis] == labels).astype(prob_dtype)[np.newaxis]
+
+    trg_vol = trg_seg = None
+    if atlas_file:
+        trg_vol = cache.get(atlas_file, "vol", add_feat_axis=True)[np.newaxis]
+        trg_seg = prob_seg(cache.get(atlas_file, "seg", add_feat_axis=True)[np.newaxis])
+    zeros = None
+    while True:
+        src_vol, src_lab = next(gen)
+        src_seg = prob_seg(src_lab)
+        if not atlas_file:
+            trg_vol, trg_lab = next(gen)
+            trg_seg = prob_seg(trg_lab)
+        if zeros is None:
+            zeros = _zero_flow(1, src_vol.shape[1:-1], zeros_dtype)
+        yield ([src_vol, trg_vol, src_seg], [trg_vol, zeros, trg_seg])
 
 
 class Prefetcher:

@@ -160,6 +160,8 @@ class VxmDense(LoadableModel):
                  src_feats=1, trg_feats=1, unet_half_res=False):
         super().__init__()
         self.training = True
+        object.__setattr__(self, "_dp", None)            # dist.TransparentDP once attached (not a submodule / buffer)
+        object.__setattr__(self, "_dp_checked", False)
         ndims = len(inshape)
         assert ndims in [1, 2, 3], 'ndims should be one of 1, 2, or 3. found: %d' % ndims
 
@@ -188,11 +190,28 @@ class VxmDense(LoadableModel):
         self.integrate = layers.VecInt(down_shape, int_steps) if int_steps > 0 else None
         self.transformer = layers.SpatialTransformer(inshape)
 
+    def _maybe_attach_dp(self):
+        """Under torchrun the model becomes data parallel by itself on its first forward (dist.TransparentDP): the
+        unmodified training loop then needs no DataParallel / DistributedDataParallel wrapper."""
+        if not self._dp_checked:
+            object.__setattr__(self, "_dp_checked", True)
+            if self.training:
+                from . import dist as vdist
+                object.__setattr__(self, "_dp", vdist.attach_if_distributed(self))
+        return self._dp
+
+    def save(self, path):
+        if self._dp is not None and not self._dp.is_writer():
+            return                       # one checkpoint per job: rank 0 writes (SURVEY 8(e))
+        super().save(path)
+
     def forward(self, source, target, registration=False):
-        if ops.conv_engine() == 'bf16':
+        self._maybe_attach_dp()
+        engine = ops.resolve_engine(self)
+        if engine in ('bf16', 'bf16x3'):
             # tensor-core engine: Unet + flow head as one hand-written forward/backward (engine_bf16.py)
             from . import engine_bf16
-            flow_field = engine_bf16.unet_flow(self, source, target)
+            flow_field = engine_bf16.unet_flow(self, source, target, split=(engine == 'bf16x3'))
         else:
             x = ops.upsample_free_cat(source, target)
             x = self.unet_model(x)

@@ -10,9 +10,34 @@ from . import _lib
 from .layers import _dims
 
 
+_default_engine = "f32"
+
+
+def set_default_engine(name):
+    """Engine used when VXM_B200_CONV_ENGINE is not set ('f32' for `import voxelmorph_b200`, 'tc' through the
+    `voxelmorph` drop-in package)."""
+    global _default_engine
+    if name not in ("f32", "bf16", "bf16x3", "tc"):
+        raise ValueError("unknown convolution engine %r" % (name,))
+    _default_engine = name
+
+
 def conv_engine():
-    """'f32' — CUDA-core fp32 parity engine; 'bf16' — tcgen05/TMEM implicit-GEMM engine."""
-    return os.environ.get("VXM_B200_CONV_ENGINE", "f32")
+    """'f32'    — CUDA-core fp32 engine (FFMA; every U-Net shape);
+    'bf16'   — tcgen05/TMEM implicit-GEMM engine, bf16 operands / fp32 accumulation (the throughput mode bench.py times);
+    'bf16x3' — the same tensor-core kernels with every operand split into a bf16 hi + lo pair and three MMAs per tile
+               (hi*hi + lo*hi + hi*lo): fp32-grade products, flow / moved image within 1e-4 of the reference;
+    'tc'     — 'bf16x3' where the tensor-core engine supports the model, else 'f32'."""
+    return os.environ.get("VXM_B200_CONV_ENGINE", _default_engine)
+
+
+def resolve_engine(model):
+    """Engine for one VxmDense forward: resolves 'tc' and falls back to f32 for shapes the tensor-core engine lacks."""
+    e = conv_engine()
+    if e == "tc":
+        from . import engine_bf16
+        return "bf16x3" if engine_bf16.supports(model) else "f32"
+    return e
 
 
 class _ConvK3Fn(torch.autograd.Function):

@@ -219,3 +219,80 @@ def conv_fwd_t(xa, xb, wpk, coutp, bias, cout, kd, up=False, out_fp32_planar=Fal
                    B, D, H, W, Ca, Cb, 1 if up else 0, cout, coutp, kd, 1 if out_fp32_planar else 0, s,
                    _lib.ptr(out2), int(split or 0), _lib.stream_ptr()), "vxm_conv3d_tc%s_fwd" % variant)
     return (out, out2) if split else out
+
+
+# ---- split-precision (bf16x3) passes ----------------------------------------------------------------------------------
+
+def split_weights(w):
+    """fp32 weights -> (hi, lo) fp32 tensors with hi = bf16(w), lo = w - hi (packed as bf16 by the weight packer)."""
+    hi = w.detach().to(torch.bfloat16).float()
+    return hi, w.detach() - hi
+
+
+def planar_to_ndhwc8_split(planes):
+    """<= 8 planar fp32 volumes -> (hi, lo) bf16 (B,D,H,W,8) tensors with hi + lo = x to 16 mantissa bits."""
+    lib = _lib.load()
+    ref = planes[0]
+    B = ref.shape[0]
+    D, H, W = (ref.shape[-3] if ref.dim() == 5 else 1), ref.shape[-2], ref.shape[-1]
+    n = len(planes)
+    arr_p = (ctypes.c_void_p * 8)(*([p.data_ptr() for p in planes] + [0] * (8 - n)))
+    arr_s = (ctypes.c_longlong * 8)(*([p.stride(0) for p in planes] + [0] * (8 - n)))
+    hi = torch.empty((B, D, H, W, 8), dtype=torch.bfloat16, device=ref.device)
+    lo = torch.empty_like(hi)
+    _lib.check(lib.vxm_planar_to_ndhwc8_split_bf16(arr_p, arr_s, n, _lib.ptr(hi), _lib.ptr(lo), B, D * H * W, _lib.stream_ptr()),
+               "vxm_planar_to_ndhwc8_split_bf16")
+    return hi, lo
+
+
+def conv_fwd_split(xa, xb, packs, bias, cout, kd, up=False, out_fp32_planar=False, slope=None):
+    """One convolution layer in split precision: three passes of the kw-stacked tcgen05 kernel accumulating
+    x_lo*w_hi + x_hi*w_lo + x_hi*w_hi in an fp32 channels-last buffer.  xa / xb: (hi, lo) pairs (or None);
+    packs: ((wpk_hi, meta), (wpk_lo, meta)) from pack_weights_t.  Returns a (hi, lo) pair of bf16 NDHWC tensors, or the
+    fp32 planar tensor when out_fp32_planar."""
+    lib = _lib.load()
+    (wh, (coutp, variant)), (wl, _) = packs
+    if variant != "s":
+        raise _lib.VxmError("split-precision convolution needs the swizzled kw-stacked kernel (VXM_B200_TC_KERNEL=auto|s)")
+    full = xb if xb is not None else xa
+    fh = full[0]
+    B, D, H, W = fh.shape[0], fh.shape[1], fh.shape[2], fh.shape[3]
+    if xb is None and up:
+        D, H, W = (D * 2 if kd == 3 else D), H * 2, W * 2
+    Ca = 0 if xa is None else xa[0].shape[-1]
+    Cb = 0 if xb is None else xb[0].shape[-1]
+    dev = fh.device
+    acc = torch.empty((B, D, H, W, coutp), dtype=torch.float32, device=dev)
+    s = -1.0 if slope is None else float(slope)
+
+    def part(x, k):
+        return None if x is None else x[k]
+
+    def launch(k_x, wpk, out, out_lo, acc_in, mode):
+        _lib.check(lib.vxm_conv3d_tcs_fwd_acc(_lib.ptr(part(xa, k_x)), _lib.ptr(part(xb, k_x)), _lib.ptr(wpk), _lib.ptr(bias),
+                                              _lib.ptr(out), _lib.ptr(out_lo), _lib.ptr(acc_in), B, D, H, W, Ca, Cb,
+                                              1 if up else 0, cout, coutp, kd, mode, s, _lib.stream_ptr()),
+                   "vxm_conv3d_tcs_fwd_acc")
+
+    launch(1, wh, acc, None, None, 2)          # x_lo * w_hi   (smallest terms first)
+    launch(0, wl, acc, None, acc, 2)           # + x_hi * w_lo
+    if out_fp32_planar:
+        out = torch.empty((B, cout, D, H, W), dtype=torch.float32, device=dev)
+        launch(0, wh, out, None, acc, 1)       # + x_hi * w_hi + bias -> fp32 planar
+        return out
+    hi = torch.empty((B, D, H, W, cout), dtype=torch.bfloat16, device=dev)
+    lo = torch.empty_like(hi)
+    launch(0, wh, hi, lo, acc, 3)              # + x_hi * w_hi + bias, activation -> (hi, lo)
+    return hi, lo
+
+
+def pool_split(x, nd):
+    lib = _lib.load()
+    xh, xl = x
+    B, D, H, W, C = xh.shape
+    Dc = D // 2 if nd == 3 else D
+    yh = torch.empty((B, Dc, H // 2, W // 2, C), dtype=torch.bfloat16, device=xh.device)
+    yl = torch.empty_like(yh)
+    _lib.check(lib.vxm_pool2_split_ndhwc_bf16(_lib.ptr(xh), _lib.ptr(xl), _lib.ptr(yh), _lib.ptr(yl), B, Dc, H // 2, W // 2, C, nd,
+                                              _lib.stream_ptr()), "vxm_pool2_split_ndhwc_bf16")
+    return yh, yl
