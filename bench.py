@@ -19,6 +19,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FULL = (160, 192, 224)
+# first-step loss vs the fp32 CPU oracle, per convolution engine (measured on B200 at 160x192x224: bf16 1.8e-7, bf16x3 2.7e-7;
+# the moved image is within 1e-4 in every mode, the flow field is what bf16 operands cost: 6e-3 vs 1.4e-5 for bf16x3)
+PARITY_TOL = {"bf16": 1e-5, "bf16x3": 1e-5, "f32": 1e-5}
 METRIC = "vol-pairs/sec (3D 160x192x224 VxmDense int_steps=7 train step, NCC+Grad, Adam)"
 UNIT = "vol-pairs/s"
 
@@ -34,6 +37,11 @@ def parse():
     ap.add_argument("--engine", default=None, choices=["f32", "bf16"], help="convolution engine (default: bf16 tensor-core engine)")
     ap.add_argument("--no-graph", action="store_true", help="time eager kernel launches instead of the captured CUDA graph")
     ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline legs")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 5], help="BASELINE.json config: 2 = the headline (default; config 3 is "
+                    "the same under torchrun), 5 = semi-supervised: + Dice on the linearly warped 30-label one-hot segmentation")
+    ap.add_argument("--no-parity", action="store_true", help="skip the first-step loss check against the CPU oracle and the bf16x3 parity-mode leg")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the reference-torch-on-GPU (eager ATen / cuDNN) baseline leg")
+    ap.add_argument("--no-c4", action="store_true", help="skip the BASELINE config 4 sweep (256^3 warp / VecInt GB/s)")
     return ap.parse_args()
 
 
@@ -128,7 +136,7 @@ class Clocks:
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference's torch CPU path on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_step_time(shape, steps, warmup, budget_s):
+def cpu_step_time(shape, steps, warmup, budget_s, min_full=1):
     """Time the oracle restatement of the reference training step (oracle/ref_torch.py: same torch CPU operators
     the reference calls) on all host cores.  Returns (sec per FULL-SIZE pair, cores, sample description)."""
     import numpy as np
@@ -168,31 +176,136 @@ def cpu_step_time(shape, steps, warmup, budget_s):
     torch.set_num_threads(cores_used)
     cores = cores_used
     est_full = t_sub / frac
-    if (steps + warmup) * est_full <= budget_s:
-        ts = run(shape, steps + warmup)[warmup:]
-        return sum(ts) / len(ts), cores, "%d full-size %s steps after %d warm-up, torch %s CPU fp32, %d threads" % (
-            len(ts), "x".join(map(str, shape)), warmup, torch.__version__, cores)
-    n = max(1, min(steps, int(budget_s / max(t_sub, 1e-3)) - warmup))
-    ts = run(sub, n + max(1, min(warmup, 2)))[max(1, min(warmup, 2)):]
+    # Full-size steps first: as many of the requested steps as fit the time budget (at least `min_full` — one is already the
+    # whole workload of the metric), after one untimed full-size warm-up when it fits too.  Only when not even that fits does
+    # the sample fall back to a sub-volume with the time scaled by the voxel ratio (never on the boxes seen so far).
+    n_fit = int(budget_s / max(est_full, 1e-3))
+    if n_fit >= min_full:
+        w = 1 if n_fit >= min_full + 1 else 0
+        n = max(min_full, min(steps, n_fit - w))
+        ts = run(shape, n + w)[w:]
+        return sum(ts) / len(ts), cores, "%d full-size %s steps after %d warm-up (of %d requested), torch %s CPU fp32, %d threads" % (
+            len(ts), "x".join(map(str, shape)), w, steps, torch.__version__, cores), True
+    n = max(1, min(steps, int(budget_s / max(t_sub, 1e-3)) - 1))
+    ts = run(sub, n + 1)[1:]
     per_full = (sum(ts) / len(ts)) / frac
     return per_full, cores, ("%d steps on a %s sub-volume (%.3f of the voxels; time scaled by 1/%.3f), torch %s CPU fp32, "
-                             "%d threads" % (len(ts), "x".join(map(str, sub)), frac, frac, torch.__version__, cores))
+                             "%d threads" % (len(ts), "x".join(map(str, sub)), frac, frac, torch.__version__, cores)), False
 
 
 def reference_arm(args):
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sec, cores, sample = cpu_step_time(tuple(args.shape), args.steps, args.warmup, budget_s=150.0)
+    sec, cores, sample, full = cpu_step_time(tuple(args.shape), args.steps, args.warmup, budget_s=150.0, min_full=3)
     v = 1.0 / sec
     line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", impl="reference",
                 config=dict(workload="3D %s VxmDense diffeomorphic (int_steps=7, int_downsize=2), NCC+0.01*Grad, Adam, batch 1"
-                            % "x".join(map(str, args.shape)), note="reference torch CPU path (oracle port) on host cores"),
+                            % "x".join(map(str, args.shape)), note="reference torch CPU path (oracle port) on host cores",
+                            same_config=bool(full), sample_steps_are_full_size=bool(full)),
                 cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind="port", sample=sample),
                 e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line), flush=True)
+
+
+
+# ------------------------------------------------------------------------------------------------
+# helper legs of the B200 arm
+# ------------------------------------------------------------------------------------------------
+CONV_SOURCES = ("conv3d_tc_s.cu", "conv3d_tc_s2.cu", "conv3d_tc_wgrad2.cu", "tc_common.cuh")
+
+
+def conv_source_hash():
+    import hashlib
+    h = hashlib.sha256()
+    for f in CONV_SOURCES:
+        with open(os.path.join(ROOT, "voxelmorph_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def default_cfg(shape):
+    return dict(inshape=tuple(shape), nb_unet_features=None, nb_unet_levels=None, unet_feat_mult=1, nb_unet_conv_per_level=1,
+                int_steps=7, int_downsize=2, bidir=False, use_probs=False, src_feats=1, trg_feats=1, unet_half_res=False)
+
+
+def oracle_first_step_loss(model, shape, S_host, T_host):
+    """Loss of the reference's step (fp32, CPU: oracle/ref_torch) on the benchmark's own initial weights and first pair."""
+    import torch
+    from oracle import ref_torch
+    sd = {k: v.detach().float().cpu().clone() for k, v in model.state_dict().items()}
+    cfg = default_cfg(shape)
+    torch.set_num_threads(max(1, min(64, os.cpu_count() or 1)))
+    with torch.no_grad():
+        y, pre = ref_torch.vxm_forward(sd, cfg, S_host, T_host)
+        return float(ref_torch.ncc_loss(T_host, y) + 0.01 * ref_torch.grad_loss(pre, "l2", 2))
+
+
+def gpu_eager_baseline(dev, shape, pairs_dev, steps=5, warmup=2):
+    """The reference's own torch path on this GPU (SURVEY 2 / BASELINE.md 4 step 5): oracle/ref_torch.train_step — the
+    same ATen / cuDNN operators voxelmorph/torch calls (nn.Conv3d, F.grid_sample, 5 x F.conv3d NCC) — eager, fp32 tensors
+    with cuDNN's default TF32 convolutions, and again with bf16 autocast around the U-Net."""
+    import torch
+    from oracle import ref_torch
+    out = {}
+    cfg = default_cfg(shape)
+    for name, ac in (("tf32_default", None), ("bf16_autocast_unet", torch.bfloat16)):
+        try:
+            sd = {k: v.to(dev).requires_grad_(True) for k, v in ref_torch.init_state_dict(cfg, seed=1234, flow_std=1e-2).items()}
+            opt = torch.optim.Adam(list(sd.values()), lr=1e-4)
+            for i in range(warmup):
+                ref_torch.train_step(sd, cfg, opt, *pairs_dev[i % len(pairs_dev)], image_loss="ncc", lam=0.01, unet_autocast=ac, sync=False)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                ref_torch.train_step(sd, cfg, opt, *pairs_dev[i % len(pairs_dev)], image_loss="ncc", lam=0.01, unet_autocast=ac, sync=False)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = dict(value=1e3 / ms, unit=UNIT, ms_per_step=ms, steps=steps, warmup=warmup,
+                             peak_mem_gb=torch.cuda.max_memory_allocated(dev) / 1e9)
+            del sd, opt
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001 - a baseline leg must not kill the bench
+            out[name] = dict(error=str(e)[:200])
+    out["what"] = ("reference torch path (oracle/ref_torch restatement of voxelmorph/torch) on the same GPU: eager ATen/cuDNN, "
+                   "torch %s, cudnn.allow_tf32=%s, device-resident pairs, CUDA events" % (torch.__version__, torch.backends.cudnn.allow_tf32))
+    return out
+
+
+def engine_leg(vxm, dev, shape, pairs_dev, engine, steps=10, warmup=3):
+    """One more timed training-step loop on a FRESH model with another convolution engine (graph-captured like the headline)."""
+    import torch
+    from voxelmorph_b200.trainer import GraphedTrainStep
+    prev = os.environ.get("VXM_B200_CONV_ENGINE")
+    os.environ["VXM_B200_CONV_ENGINE"] = engine
+    try:
+        torch.manual_seed(1234)
+        model = vxm.networks.VxmDense(inshape=shape, int_steps=7, int_downsize=2)
+        with torch.no_grad():
+            model.flow.weight.normal_(0, 1e-2)
+        model.to(dev).train()
+        opt = vxm.optim.FusedAdam(model.parameters(), lr=1e-4)
+        step = GraphedTrainStep(model, opt, image_loss="ncc", lam=0.01, int_downsize=2).capture(*pairs_dev[0])
+        for i in range(warmup):
+            step(*pairs_dev[i % len(pairs_dev)])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step(*pairs_dev[i % len(pairs_dev)])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return dict(engine=engine, value=1e3 / ms, unit=UNIT, ms_per_step=ms, steps=steps, warmup=warmup, cuda_graph=True)
+    finally:
+        if prev is None:
+            os.environ.pop("VXM_B200_CONV_ENGINE", None)
+        else:
+            os.environ["VXM_B200_CONV_ENGINE"] = prev
 
 
 # ------------------------------------------------------------------------------------------------
@@ -206,6 +319,7 @@ def b200_arm(args):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback; use --impl reference for the CPU arm)")
+    os.environ["VXM_B200_TRANSPARENT_DP"] = "0"     # bench drives its one allreduce per step itself (inside the CUDA graph)
     world, rank, local = vdist.init_from_env()
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
@@ -220,9 +334,16 @@ def b200_arm(args):
 
     # ---- model, optimizer, data ----------------------------------------------------------------
     torch.manual_seed(1234)
-    model = vxm.networks.VxmDense(inshape=shape, int_steps=7, int_downsize=2)
+    semi = args.config == 5
+    NLAB = 30
+    if semi:
+        model = vxm.networks.VxmDenseSemiSupervisedSeg(shape, NLAB, int_steps=7, int_downsize=2)
+        flow_head = model.vxm_model.flow
+    else:
+        model = vxm.networks.VxmDense(inshape=shape, int_steps=7, int_downsize=2)
+        flow_head = model.flow
     with torch.no_grad():
-        model.flow.weight.normal_(0, 1e-2)   # trained-like flow scale so that warps / VecInt do real work
+        flow_head.weight.normal_(0, 1e-2)   # trained-like flow scale so that warps / VecInt do real work
     model.to(dev).train()
     opt = vxm.optim.FusedAdam(model.parameters(), lr=1e-4, world_size=world)
     vdist.broadcast_params(opt.fp.flat)
@@ -241,14 +362,52 @@ def b200_arm(args):
         fl = torch.nn.functional.interpolate(torch.randn((1, 3, shape[0] // 16, shape[1] // 16, shape[2] // 16), generator=g,
                                                          device=dev) * 3.0, size=shape, mode="trilinear", align_corners=True)
         trg = st(src, fl.contiguous())
-        pairs_host.append((src.cpu().pin_memory(), trg.cpu().pin_memory()))
-    pairs_dev = [(s.to(dev), t.to(dev)) for s, t in pairs_host]
+        sample = [src, trg]
+        if semi:
+            # synthetic anatomy: NLAB smooth blobs -> label map at half resolution -> one-hot (1, 30, 80, 96, 112) for both images
+            # (generators.semisupervised: [::2] sub-sampled one-hot of the label map); the target's labels are the source's
+            # moved by the same flow (nearest), so the Dice term has something to align
+            half = tuple(d // 2 for d in shape)
+            blobs = torch.nn.functional.interpolate(torch.randn((1, NLAB, shape[0] // 16, shape[1] // 16, shape[2] // 16), generator=g, device=dev),
+                                                    size=shape, mode="trilinear", align_corners=True)
+            lab_s = blobs.argmax(1, keepdim=True).float()
+            lab_t = vxm.layers.SpatialTransformer(shape, mode="nearest")(lab_s, fl.contiguous())
+            oh = lambda lab: (lab[:, :, ::2, ::2, ::2] == torch.arange(NLAB, device=dev).view(1, NLAB, 1, 1, 1)).float().contiguous()  # noqa: E731
+            sample += [oh(lab_s), oh(lab_t)]
+            del blobs, lab_s, lab_t
+        pairs_host.append(tuple(x.cpu().pin_memory() for x in sample))
+    pairs_dev = [tuple(x.to(dev) for x in smp) for smp in pairs_host]
+    dice = vxm.losses.Dice().loss
+
+    def forward_loss(*inp):
+        if semi:
+            y, pre, yseg = model(inp[0], inp[1], inp[2])
+            return ncc(inp[1], y) + 0.01 * grad(None, pre) + 0.01 * dice(inp[3], yseg)
+        y, flow = model(inp[0], inp[1])
+        return ncc(inp[1], y) + 0.01 * grad(None, flow)
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
 
-    def eager_step(S, T):
+    # ---- parity of the timed configuration at its own size: first-step loss vs the CPU oracle -------------------------
+    parity = None
+    if rank == 0 and not args.no_parity and not semi:
+        with torch.no_grad():
+            y0, f0 = model(*pairs_dev[0])
+            loss_gpu = float(ncc(pairs_dev[0][1], y0) + 0.01 * grad(None, f0))
+        del y0, f0
+        loss_ref = oracle_first_step_loss(model, shape, pairs_host[0][0], pairs_host[0][1])
+        tol = PARITY_TOL.get(os.environ["VXM_B200_CONV_ENGINE"], 1e-4)
+        err = abs(loss_gpu - loss_ref) / abs(loss_ref)
+        parity = dict(loss_gpu=loss_gpu, loss_oracle=loss_ref, rel_err=err, tol=tol, ok=bool(err <= tol),
+                      what="NCC + 0.01 Grad of the first pair on the initial weights: timed engine vs oracle/ref_torch (fp32 CPU "
+                           "restatement of the reference); the full forward / gradient comparison at this size is "
+                           "tests/test_gpu_bf16_engine.py::test_full_size_step_vs_oracle")
+        if not parity["ok"]:
+            raise SystemExit("bench.py: first-step loss %.6f deviates from the oracle's %.6f by %.2e (> %.1e): the timed path is "
+                             "not computing the reference's step" % (loss_gpu, loss_ref, err, tol))
+
+    def eager_step(*inp):
         opt.zero_grad()
-        y, flow = model(S, T)
-        loss = ncc(T, y) + 0.01 * grad(None, flow)
+        loss = forward_loss(*inp)
         loss.backward()
         vdist.allreduce_grads(opt.fp.grad)
         opt.step()
@@ -257,14 +416,16 @@ def b200_arm(args):
     # the whole step (zero-grad, fwd, losses, bwd, allreduce, Adam) captured once in a CUDA graph and replayed
     step, graphed = eager_step, False
     launches_per_step = None
+    trainer_ref = []
     if not args.no_graph:
         from voxelmorph_b200.trainer import GraphedTrainStep
         try:
             n0 = vxm._lib.launch_count()
             eager_step(*pairs_dev[0])
             launches_per_step = vxm._lib.launch_count() - n0
-            trainer = GraphedTrainStep(model, opt, image_loss="ncc", lam=0.01, int_downsize=2).capture(*pairs_dev[0])
+            trainer = GraphedTrainStep(model, opt, loss_fn=lambda m, *inp: forward_loss(*inp)).capture(*pairs_dev[0])
             step, graphed = trainer, True
+            trainer_ref.append(trainer)
         except Exception as e:  # noqa: BLE001 - report and fall back to eager launches
             print("bench.py: CUDA graph capture failed (%s); timing eager launches" % e, file=sys.stderr)
 
@@ -301,7 +462,7 @@ def b200_arm(args):
 
     # ---- end-to-end: host buffers, H2D of the pair + D2H of the loss inside the timed region --------
     copy_stream = torch.cuda.Stream(device=dev)
-    bufs = [(torch.empty_like(pairs_dev[0][0]), torch.empty_like(pairs_dev[0][1])) for _ in range(2)]
+    bufs = [tuple(torch.empty_like(x) for x in pairs_dev[0]) for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
 
@@ -309,8 +470,8 @@ def b200_arm(args):
         b = i % 2
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(freed[b])
-            bufs[b][0].copy_(pairs_host[i % NPAIR][0], non_blocking=True)
-            bufs[b][1].copy_(pairs_host[i % NPAIR][1], non_blocking=True)
+            for dst, srcbuf in zip(bufs[b], pairs_host[i % NPAIR]):
+                dst.copy_(srcbuf, non_blocking=True)
             ready[b].record(copy_stream)
 
     for b in range(2):
@@ -329,7 +490,7 @@ def b200_arm(args):
     e1.record()
     barrier()
     ms_e2e = vdist.max_over_ranks(e0.elapsed_time(e1), dev)
-    e2e = dict(value=world * K / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=2 * V * 4, d2h_bytes_per_step=4,
+    e2e = dict(value=world * K / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=int(sum(x.numel() * 4 for x in pairs_host[0])), d2h_bytes_per_step=4,
                ms_per_step=ms_e2e / K, api="voxelmorph_b200.networks.VxmDense + losses.NCC/Grad + optim.FusedAdam, pinned host "
                "buffers, H2D double-buffered on a copy stream")
 
@@ -404,22 +565,46 @@ def b200_arm(args):
     # DRAM traffic of the conv family per step: taken from the committed ncu pass over this same command
     # (profiles/r1_traffic.json; ncu cannot run inside a timed bench), valid for the full-size bf16 workload only.
     traffic, traffic_src = None, None
-    tj = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")
+    tj = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if engine == "bf16" and tuple(shape) == (160, 192, 224) and os.path.exists(tj):
         with open(tj) as f:
             tinfo = json.load(f)
-        traffic, traffic_src = tinfo["conv_dram_mbytes_per_step"] * 1e6, tinfo["source"]
+        if tinfo.get("conv_source_sha") == conv_source_hash():
+            traffic, traffic_src = tinfo["conv_dram_mbytes_per_step"] * 1e6, tinfo["source"]
+        else:
+            traffic_src = ("stale: profiles/r2_traffic.json was captured for conv sources %s, the library was built from %s"
+                           % (tinfo.get("conv_source_sha"), conv_source_hash()))
     roofline = dict(bound="tensor", kernel="conv3d k3 fwd+dgrad+wgrad, all 12 layers (%s)" % ("tcgen05 bf16 implicit GEMM" if engine == "bf16" else "fp32 FFMA engine"),
-                    achieved=ach, peak=peaks["tf_sus"], unit="TFLOP/s", frac=ach / peaks["tf_sus"], traffic=traffic, traffic_unit="bytes per step (all conv launches)", traffic_source=traffic_src,
-                    peak_source=peaks["source"] + ", sustained bf16", ms_per_step=conv_total_ms, conv_launches=n_conv_launches,
+                    achieved=ach, peak=peaks["tf_burst"], unit="TFLOP/s", frac=ach / peaks["tf_burst"], traffic=traffic, traffic_unit="bytes per step (all conv launches)", traffic_source=traffic_src,
+                    peak_source=peaks["source"] + ", burst bf16 (the conv launches are replayed in isolation behind a sleep, not inside the long step)",
+                    frac_of_sustained=ach / peaks["tf_sus"], ms_per_step=conv_total_ms, conv_launches=n_conv_launches,
                     share_of_step=conv_total_ms / (ms / K), flops_per_step=flops_step)
 
-    kernels = {} if args.no_kernels else kernel_rooflines(vxm, dev, shape, peaks)
+    kernels = {} if (args.no_kernels or semi) else kernel_rooflines(vxm, dev, shape, peaks)
+    parity_mode = None
+    if not args.no_parity and engine == "bf16" and world == 1 and not semi:
+        try:
+            parity_mode = engine_leg(vxm, dev, shape, pairs_dev, "bf16x3")
+            parity_mode["note"] = ("same step with the split-precision tensor-core forward (3 tcgen05 passes per layer, flow / moved image "
+                                   "within 1e-4 of the fp32 reference: tests/test_gpu_bf16_engine.py); backward on bf16 operands")
+        except Exception as e:  # noqa: BLE001
+            parity_mode = dict(error=str(e)[:300])
+    c4 = None
+    if not args.no_c4 and world == 1 and not semi:
+        try:
+            c4 = c4_sweep(vxm, dev, peaks)
+        except Exception as e:  # noqa: BLE001
+            c4 = dict(error=str(e)[:300])
+    gpu_eager = None
+    if not args.no_gpu_eager and world == 1 and not semi:
+        del trainer_ref[:]
+        torch.cuda.empty_cache()
+        gpu_eager = gpu_eager_baseline(dev, shape, pairs_dev)
 
     # ---- CPU baseline (oracle port of the reference's torch CPU path) -------------------------------
     cpu = None
     if not args.no_cpu_baseline:
-        sec, cores, sample = cpu_step_time(shape, 1, 0, budget_s=30.0)
+        sec, cores, sample, _ = cpu_step_time(shape, 1, 0, budget_s=30.0)
         cpu = dict(value=1.0 / sec, unit=UNIT, cores=cores, kind="port", sample=sample)
 
     act_gb = 4.0 * V * (2 + 16 + 48 + 32 + 16 + 16 + 3) / 1e9
@@ -427,14 +612,17 @@ def b200_arm(args):
                 higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32" if engine == "f32" else "bf16 (conv operands) / f32 (accumulate, warp, VecInt, losses)",
                 data="synthetic", impl="b200",
-                config=dict(workload="3D %s VxmDense diffeomorphic (int_steps=7, int_downsize=2), default U-Net features, "
-                            "NCC(9^3)+0.01*Grad(l2), Adam lr 1e-4, 1 pair per GPU" % "x".join(map(str, shape)),
+                config=dict(workload=("3D %s VxmDense diffeomorphic (int_steps=7, int_downsize=2), default U-Net features, "
+                                      "NCC(9^3)+0.01*Grad(l2), Adam lr 1e-4, 1 pair per GPU" % "x".join(map(str, shape)))
+                            + (" + semi-supervised branch (BASELINE config 5): 30-label one-hot segmentations at half resolution warped "
+                               "linearly, + 0.01*Dice" if semi else ""), baseline_config=args.config,
                             global_batch=world, parallelism="dp%d (one flat-gradient allreduce per step)" % world,
                             conv_engine=engine, cuda_graph=graphed,
                             l2="inputs rotate over %d resident pairs; per-step working set ~%.1f GB of full-resolution "
                                "activations >> 126 MB L2, so no explicit flush" % (NPAIR, act_gb)),
                 clocks=clk, e2e=e2e, gpu_launches=int(launches), launches_per_step=launches / K,
-                roofline=roofline, kernels=kernels, cpu_baseline=cpu)
+                roofline=roofline, kernels=kernels, cpu_baseline=cpu, parity_check=parity, parity_mode=parity_mode,
+                gpu_eager_baseline=gpu_eager, c4_sweep=c4)
     print(json.dumps(line), flush=True)
     _leave(world, rank)
 
@@ -544,6 +732,55 @@ def kernel_rooflines(vxm, dev, shape, peaks):
     Jg = J.clone().requires_grad_(True)
     timeit(lambda: ncc(I, Jg), V * 8 + V * 12, "ncc_fwd_training", "forward that also stores the 3 fields the backward box-filters")
     timeit_bwd(lambda: (ncc(I, Jg), torch.ones((), device=dev)), V * 12 + V * 12, "ncc_bwd", "reads I, J + 3 saved fields, writes dJ")
+    return out
+
+
+def c4_sweep(vxm, dev, peaks):
+    """BASELINE config 4: inference-only SpatialTransformer + VecInt throughput sweep at 256^3 / 128^3,
+    fp32, white-noise flows of std sigma voxels.  GB/s are algorithmic bytes / CUDA-event time."""
+    import torch
+    full, half = (256,) * 3, (128,) * 3
+    V, Vh = 256 ** 3, 128 ** 3
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    out = dict(warp={}, vecint={}, note="256^3 warp: src rand (1,C,256^3), flow randn*sigma; VecInt on randn*2 fields (1..B,3,S^3); "
+               "3 warm-up + 5 timed launches, 256 MB L2 flush between launches; frac = GB/s / measured copy peak")
+
+    def timeit(fn, nbytes):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(5):
+            flush.zero_()
+            torch.cuda._sleep(300000)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        t = statistics.median(ts)
+        gbs = nbytes / (t * 1e-3) / 1e9
+        return dict(us=round(t * 1e3, 1), gbs=round(gbs, 1), frac=round(gbs / peaks["hbm"], 3))
+
+    with torch.no_grad():
+        noise = torch.randn((1, 3) + full, device=dev)
+        for C in (1, 3, 30):
+            src = torch.rand((1, C) + full, device=dev)
+            for mode in ("bilinear", "nearest"):
+                st = vxm.layers.SpatialTransformer(full, mode=mode)
+                for sigma in (0, 1, 4, 16):
+                    flow = noise * float(sigma)
+                    out["warp"]["C%d_%s_sigma%d" % (C, mode, sigma)] = timeit(lambda: st(src, flow), V * (8 * C + 12))
+                    del flow
+            del src
+        del noise
+        for S, Vs in ((128, Vh), (256, V)):
+            for B in (1, 2, 4):
+                vel = torch.randn((B, 3) + (S,) * 3, device=dev) * 2.0
+                for n in range(1, 8):
+                    vi = vxm.layers.VecInt((S,) * 3, n)
+                    out["vecint"]["S%d_B%d_n%d" % (S, B, n)] = timeit(lambda: vi(vel), B * Vs * 24 * n)
+                del vel
     return out
 
 

@@ -84,6 +84,9 @@ int vxm_vecint_bwd(const float* grad_out, const float* states, float* grad_vel, 
  * vxm_vecint_fast_work_bytes(backward) bytes (2 float4 fields forward without states, 3 backward). */
 size_t vxm_vecint_fast_states_bytes(int B, int D, int H, int W, int nsteps);
 size_t vxm_vecint_fast_work_bytes(int B, int D, int H, int W, int backward);
+/* measurement aid: a cooperative launch (512 threads per CTA, `ctas_per_sm` CTAs per SM or the occupancy limit when 0)
+ * that executes `nsync` grid-wide synchronisations and nothing else */
+int vxm_debug_gridsync(int nsync, int ctas_per_sm, void* stream);
 
 /* ---- ResizeTransform: reference voxelmorph/torch/layers.py:85-97 (F.interpolate :88,:94) ----
  * out = post * lerp(pre * x) with align_corners=True linear interpolation.
@@ -104,6 +107,11 @@ int vxm_ncc_fwd(const float* I, const float* J, float* loss, float* saved, void*
 /* grad_J = grad_loss[0] * d(-mean cc)/dJ.  grad_loss is a device scalar. */
 int vxm_ncc_bwd(const float* I, const float* J, const float* saved, const float* grad_loss,
                 float* grad_J, int B, int D, int H, int W, int wd, int wh, int ww, void* stream);
+
+/* ---- Jacobian determinant of x -> x + disp(x): reference voxelmorph/py/utils.py:473-516 (numpy, np.gradient) ----
+ * disp: (B,nd,D,H,W) displacement in voxels (the layout VxmDense(registration=True) returns).  det (B,D,H,W), may be NULL;
+ * folds (one uint64, may be NULL) receives the number of voxels with det <= 0. */
+int vxm_jacdet(const float* disp, float* det, unsigned long long* folds, int B, int D, int H, int W, int nd, void* stream);
 
 /* ---- Grad: reference voxelmorph/torch/losses.py:102-135 ----
  * y: (B,nd,D,H,W) (any channel count C).  penalty 1 = l1, 2 = l2.  loss[0] = mult * mean_b mean_axes mean |dy|^p */
@@ -180,6 +188,13 @@ int vxm_conv3d_tct_fwd(const void* xa, const void* xb, const void* wpk, const fl
 size_t vxm_conv3d_tcs_packed_bytes(int cin_eff, int coutp, int kd);
 int vxm_conv3d_tcs_pack(const float* w, void* wpk, int Cout, int Cin, int kd, int coutp, int transposed, void* stream);
 int vxm_conv3d_tcs_supported(int Ca, int Cb, int Cout);
+/* every packed operand of a model in ONE launch: the caller fills an array of descriptors on the host
+ * (vxm_conv3d_tcs_pack_desc_bytes() bytes each; vxm_conv3d_tcs_pack_desc returns the operand's element count so that
+ * `begin` can be chained), uploads it once and calls vxm_conv3d_tcs_pack_multi with the summed element count. */
+size_t vxm_conv3d_tcs_pack_desc_bytes(void);
+int vxm_conv3d_tcs_pack_desc(void* desc_host, const float* w, void* wpk, int Cout, int Cin, int kd, int coutp, int transposed,
+                             int begin);
+int vxm_conv3d_tcs_pack_multi(const void* descs_dev, int ndesc, int total, void* stream);
 int vxm_conv3d_tcs_fwd(const void* xa, const void* xb, const void* wpk, const float* bias, void* out, const void* mask,
                        int B, int D, int H, int W, int Ca, int Cb, int up, int Cout, int coutp, int kd, int out_mode,
                        float slope, void* out2, int csplit, void* stream);

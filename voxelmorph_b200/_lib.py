@@ -29,11 +29,13 @@ SIGNATURES = {
     "vxm_vecint_bwd": (c_i, [c_f, c_f, c_f, c_f] + [c_i] * 7 + [c_f]),
     "vxm_vecint_fast_states_bytes": (c_sz, [c_i] * 5),
     "vxm_vecint_fast_work_bytes": (c_sz, [c_i] * 5),
+    "vxm_debug_gridsync": (c_i, [c_i, c_i, c_f]),
     "vxm_resize_fwd": (c_i, [c_f, c_f] + [c_i] * 8 + [c_fl, c_fl, c_f]),
     "vxm_resize_bwd": (c_i, [c_f, c_f] + [c_i] * 8 + [c_fl, c_fl, c_f]),
     "vxm_ncc_workspace_bytes": (c_sz, [c_i] * 4),
     "vxm_ncc_fwd": (c_i, [c_f, c_f, c_f, c_f, c_f] + [c_i] * 7 + [c_f]),
     "vxm_ncc_bwd": (c_i, [c_f, c_f, c_f, c_f, c_f] + [c_i] * 7 + [c_f]),
+    "vxm_jacdet": (c_i, [c_f, c_f, c_f] + [c_i] * 5 + [c_f]),
     "vxm_reduce_workspace_bytes": (c_sz, []),
     "vxm_gradloss_fwd": (c_i, [c_f, c_f, c_f] + [c_i] * 7 + [c_fl, c_f]),
     "vxm_gradloss_bwd": (c_i, [c_f, c_f, c_f] + [c_i] * 7 + [c_fl, c_f]),
@@ -55,6 +57,9 @@ SIGNATURES = {
     "vxm_conv3d_tcs_packed_bytes": (c_sz, [c_i] * 3),
     "vxm_conv3d_tcs_pack": (c_i, [c_f, c_f] + [c_i] * 5 + [c_f]),
     "vxm_conv3d_tcs_supported": (c_i, [c_i] * 3),
+    "vxm_conv3d_tcs_pack_desc_bytes": (c_sz, []),
+    "vxm_conv3d_tcs_pack_desc": (c_i, [c_f, c_f, c_f] + [c_i] * 6),
+    "vxm_conv3d_tcs_pack_multi": (c_i, [c_f, c_i, c_i, c_f]),
     "vxm_conv3d_tcs_fwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f] + [c_i] * 11 + [c_fl, c_f, c_i, c_f]),
     "vxm_conv3d_tcs2_fwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f] + [c_i] * 11 + [c_fl, c_f, c_i, c_f]),
     "vxm_conv3d_tcs_fwd_acc": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_f] + [c_i] * 11 + [c_fl, c_f]),

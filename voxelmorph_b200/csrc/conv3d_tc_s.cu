@@ -8,6 +8,8 @@
 // channels are split into at most two groups of 16 / 32 / 64 channels (48 = 32 + 16), each with its own slab region.
 // A (kd, kh) tap shifts the A operand by whole 32-voxel rows (a multiple of the 8-row swizzle period), so the start
 // address stays pattern-aligned and the descriptor base offset is 0.
+#include <string.h>
+
 #include "tc_common.cuh"
 
 namespace vxm {
@@ -27,11 +29,11 @@ struct ConvSArgs {
   // split-precision (bf16x3) passes: `acc_in` (fp32 channels-last, COUT channels per voxel) is added to the tile before the
   // epilogue; out_mode 2 stores the raw fp32 sums back in that layout (no bias / activation), out_mode 3 applies bias +
   // activation and stores the result as a bf16 (hi, lo) pair: hi -> out, lo = bf16(x - hi) -> out_lo
-  const float* acc_in; void* out_lo;
   int B, D, H, W, Ca, Cb, up, upd, Cout, out_mode;
   float slope;
   int tiles_h, tiles_w, dchunk, nchunks, nitems, nslot;
   uint32_t wbytes;
+  const float* acc_in; void* out_lo;
 };
 
 // byte offset inside a swizzled K-major tile whose rows are `width` bytes (32, 64 or 128): Swizzle<log2(width/16),4,3>
@@ -50,7 +52,9 @@ __device__ __forceinline__ uint64_t make_desc_kmajor_swz(uint32_t saddr, uint32_
 
 // HT = 8: one slab step feeds TWO 4-row accumulators (one per epilogue group), halving the per-step issue / barrier
 // overhead that bounds the thin layers and cutting the halo re-reads from 1.5x to 1.25x.
-template <int KD, int G0, int G1, int COUT, int HT>
+// ACC: the split-precision epilogue (acc_in / out_mode 2, 3) is compiled in; the plain kernels (ACC = false) keep the
+// round-1 epilogue — with the extra live registers the 32-channel variants spilled and lost up to 1.8x.
+template <int KD, int G0, int G1, int COUT, int HT, bool ACC>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const ConvSArgs a) {
   constexpr int SROWS = (HT + 2) * WT;
   constexpr int NH = HT / 4;
@@ -273,11 +277,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const ConvSArgs a
 #pragma unroll
         for (int c0 = 0; c0 < COUT; c0 += 16) {
           uint32_t r0[16], r1[16], r2[16];
-          float4 ain[4];
-          if (a.acc_in && valid) {      // partial sums of the earlier split-precision passes (issued before the TMEM wait)
-            const float4* ap = reinterpret_cast<const float4*>(a.acc_in + vox * COUT + c0);
+          [[maybe_unused]] float4 ain[ACC ? 4 : 1];
+          if constexpr (ACC) {
+            if (a.acc_in && valid) {      // partial sums of the earlier split-precision passes (issued before the TMEM wait)
+              const float4* ap = reinterpret_cast<const float4*>(a.acc_in + vox * COUT + c0);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) ain[q] = __ldg(ap + q);
+              for (int q = 0; q < 4; ++q) ain[q] = __ldg(ap + q);
+            }
           }
           tmem_ld16(taddr + c0, r0);
           tmem_ld16(taddr + COUT + c0, r1);
@@ -294,37 +300,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const ConvSArgs a
             const float p2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[c]), 1);
             v[c] = (p0 + __uint_as_float(r1[c])) + p2;      // out[w'] = P0[w'-1] + P1[w'] + P2[w'+1]
           }
-          if (a.acc_in && valid) {
+          bool handled = false;
+          if constexpr (ACC) {
+            if (a.acc_in && valid) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { v[4 * q] += ain[q].x; v[4 * q + 1] += ain[q].y; v[4 * q + 2] += ain[q].z; v[4 * q + 3] += ain[q].w; }
-          }
-          if (a.out_mode == 2) {
-            if (valid) {
-              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + vox * COUT + c0);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              for (int q = 0; q < 4; ++q) { v[4 * q] += ain[q].x; v[4 * q + 1] += ain[q].y; v[4 * q + 2] += ain[q].z; v[4 * q + 3] += ain[q].w; }
             }
-          } else if (a.out_mode == 3) {
-            if (valid && c0 < a.Cout) {
+            if (a.out_mode == 2) {
+              handled = true;
+              if (valid) {
+                float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + vox * COUT + c0);
 #pragma unroll
-              for (int q = 0; q < 16; q += 8) {
-                if (c0 + q < a.Cout) {
-                  uint32_t hi[4], lo[4];
+                for (int q = 0; q < 4; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              }
+            } else if (a.out_mode == 3) {
+              handled = true;
+              if (valid && c0 < a.Cout) {
 #pragma unroll
-                  for (int e = 0; e < 8; e += 2) {
-                    float x0 = v[q + e] + bias_at(c0 + q + e), x1 = v[q + e + 1] + bias_at(c0 + q + e + 1);
-                    if (a.slope >= 0.f) { x0 = x0 >= 0.f ? x0 : x0 * a.slope; x1 = x1 >= 0.f ? x1 : x1 * a.slope; }
-                    const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-                    hi[e >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                    lo[e >> 1] = pack_bf16x2(x0 - __bfloat162float(h0), x1 - __bfloat162float(h1));
+                for (int q = 0; q < 16; q += 8) {
+                  if (c0 + q < a.Cout) {
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) {
+                      float x0 = v[q + e] + bias_at(c0 + q + e), x1 = v[q + e + 1] + bias_at(c0 + q + e + 1);
+                      if (a.slope >= 0.f) { x0 = x0 >= 0.f ? x0 : x0 * a.slope; x1 = x1 >= 0.f ? x1 : x1 * a.slope; }
+                      const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                      hi[e >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                      lo[e >> 1] = pack_bf16x2(x0 - __bfloat162float(h0), x1 - __bfloat162float(h1));
+                    }
+                    const size_t o = vox * a.Cout + c0 + q;
+                    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out_lo) + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                   }
-                  const size_t o = vox * a.Cout + c0 + q;
-                  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out_lo) + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                 }
               }
             }
-          } else if (valid && c0 < a.Cout) {
+          }
+          if (!handled && valid && c0 < a.Cout) {
             if (a.out_mode == 0) {
 #pragma unroll
               for (int q = 0; q < 16; q += 8) {
@@ -398,6 +410,41 @@ __global__ void pack_weights_s_kernel(const float* __restrict__ w, __nv_bfloat16
   }
 }
 
+// All packed operands of a model in ONE launch (23 pack launches per training step otherwise: forward + transposed copy
+// of every layer, a few kilobytes each).  `descs` lives in device memory; element ranges are consecutive.
+struct PackDesc {
+  const float* w;
+  __nv_bfloat16* out;
+  int Cout, Cin, KD, COUT, NN, G0, G1, transposed;
+  int begin, count;      // global element range [begin, begin + count)
+};
+__global__ void pack_weights_multi_kernel(const PackDesc* __restrict__ descs, int ndesc, int total) {
+  for (int gi = blockIdx.x * blockDim.x + threadIdx.x; gi < total; gi += gridDim.x * blockDim.x) {
+    int lo = 0, hi = ndesc - 1;
+    while (lo < hi) {                         // last descriptor whose begin <= gi
+      const int mid = (lo + hi + 1) >> 1;
+      if (descs[mid].begin <= gi) lo = mid; else hi = mid - 1;
+    }
+    const PackDesc d = descs[lo];
+    const int i = gi - d.begin;
+    const int T = d.KD * 9, CG = d.G0 + d.G1;
+    const int ci = i % CG, n = (i / CG) % d.NN, st = i / (CG * d.NN);
+    const int kd = st / 3, kh = st % 3, g = n / d.COUT, co = n % d.COUT;
+    const int tap = (kd * 3 + kh) * 3 + g;
+    float v = 0.f;
+    if (!d.transposed) {
+      if (co < d.Cout && ci < d.Cin) v = d.w[((size_t)co * d.Cin + ci) * T + tap];
+    } else {
+      if (co < d.Cin && ci < d.Cout) v = d.w[((size_t)ci * d.Cin + co) * T + (T - 1 - tap)];
+    }
+    const uint32_t W0 = d.G0 * 2, W1 = d.G1 * 2;
+    uint32_t off;
+    if (ci < d.G0) off = swz((uint32_t)n * W0 + (uint32_t)ci * 2u, W0);
+    else off = (uint32_t)d.NN * W0 + swz((uint32_t)n * W1 + (uint32_t)(ci - d.G0) * 2u, W1);
+    d.out[((size_t)st * d.NN * (W0 + W1) + off) / 2] = __float2bfloat16_rn(v);
+  }
+}
+
 // channel grouping of a convolution input of `cin` channels (8 counts as a zero-padded 16)
 static void groups_of(int cin, int* g0, int* g1) {
   if (cin == 8 || cin == 16) { *g0 = 16; *g1 = 0; }
@@ -429,6 +476,31 @@ extern "C" int vxm_conv3d_tcs_pack(const float* w, void* wpk, int Cout, int Cin,
   int total = kd * 3 * NN * (g0 + g1);
   pack_weights_s_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(w, (__nv_bfloat16*)wpk, Cout, Cin, kd, coutp, NN, g0, g1, transposed);
   return check_launch("conv3d_tcs_pack");
+}
+
+extern "C" size_t vxm_conv3d_tcs_pack_desc_bytes(void) { return sizeof(PackDesc); }
+
+// Fill one host-side descriptor (the caller uploads the array once and keeps it while the pointers stay valid).
+extern "C" int vxm_conv3d_tcs_pack_desc(void* desc_host, const float* w, void* wpk, int Cout, int Cin, int kd, int coutp, int transposed,
+                                        int begin) {
+  VXM_REQUIRE(desc_host && w && wpk && Cout > 0 && Cin > 0 && (kd == 1 || kd == 3) && (coutp == 16 || coutp == 32 || coutp == 48 || coutp == 64),
+              "conv3d_tcs_pack_desc: bad argument");
+  const int cin_eff = transposed ? Cout : Cin, nout = transposed ? Cin : Cout;
+  VXM_REQUIRE(nout <= coutp && cin_eff <= 64, "conv3d_tcs_pack_desc: channel counts do not fit");
+  int g0, g1;
+  groups_of(cin_eff <= 8 ? 8 : (cin_eff <= 16 ? 16 : (cin_eff <= 32 ? 32 : (cin_eff <= 48 ? 48 : 64))), &g0, &g1);
+  PackDesc d;
+  d.w = w; d.out = (__nv_bfloat16*)wpk; d.Cout = Cout; d.Cin = Cin; d.KD = kd; d.COUT = coutp; d.NN = 3 * coutp; d.G0 = g0; d.G1 = g1;
+  d.transposed = transposed; d.begin = begin; d.count = kd * 3 * d.NN * (g0 + g1);
+  memcpy(desc_host, &d, sizeof(d));
+  return d.count;      // elements of this operand (>= 0), so the caller can chain `begin`
+}
+
+extern "C" int vxm_conv3d_tcs_pack_multi(const void* descs_dev, int ndesc, int total, void* stream) {
+  VXM_REQUIRE(descs_dev && ndesc > 0 && total > 0, "conv3d_tcs_pack_multi: bad argument");
+  const int blocks = (total + 255) / 256, cap = sm_count() * 8;
+  pack_weights_multi_kernel<<<blocks < cap ? blocks : cap, 256, 0, as_stream(stream)>>>((const PackDesc*)descs_dev, ndesc, total);
+  return check_launch("conv3d_tcs_pack_multi");
 }
 
 extern "C" int vxm_conv3d_tcs_supported(int Ca, int Cb, int Cout) {
@@ -511,10 +583,16 @@ static int conv_tcs_launch(const void* xa, const void* xb, const void* wpk, cons
   size_t smem = fixed + (size_t)nslot * slab;
   int grid = a.nitems < nsm ? a.nitems : nsm;
   cudaStream_t st = as_stream(stream);
+  const bool acc_epi = acc_in != nullptr || out_mode >= 2;
 #define VXM_TCS_LAUNCH(KD_, G0_, G1_, CO_, HT_)                                                                                   \
   do {                                                                                                                            \
-    VXM_CUDA(cudaFuncSetAttribute(conv_tcs_kernel<KD_, G0_, G1_, CO_, HT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    conv_tcs_kernel<KD_, G0_, G1_, CO_, HT_><<<grid, NTHREADS, smem, st>>>(a);                                                     \
+    if (acc_epi) {                                                                                                                \
+      VXM_CUDA(cudaFuncSetAttribute(conv_tcs_kernel<KD_, G0_, G1_, CO_, HT_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      conv_tcs_kernel<KD_, G0_, G1_, CO_, HT_, true><<<grid, NTHREADS, smem, st>>>(a);                                            \
+    } else {                                                                                                                      \
+      VXM_CUDA(cudaFuncSetAttribute(conv_tcs_kernel<KD_, G0_, G1_, CO_, HT_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      conv_tcs_kernel<KD_, G0_, G1_, CO_, HT_, false><<<grid, NTHREADS, smem, st>>>(a);                                           \
+    }                                                                                                                             \
   } while (0)
 #define VXM_TCS_G8(KD_, CO_)                                                  \
   do {                                                                        \

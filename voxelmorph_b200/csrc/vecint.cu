@@ -389,6 +389,13 @@ __global__ void __launch_bounds__(512) vecint_bwd_fast_kernel(const float* __res
   }
 }
 
+// measurement aid (tools/r2_memprof.py): a cooperative launch of the same shape that only synchronises
+__global__ void __launch_bounds__(512) gridsync_probe_kernel(int nsync, unsigned* sink) {
+  cg::grid_group grid = cg::this_grid();
+  for (int i = 0; i < nsync; ++i) grid.sync();
+  if (sink && blockIdx.x == 0 && threadIdx.x == 0) *sink = (unsigned)nsync;
+}
+
 static VecFast make_vfast(int B, int D, int H, int W) {
   VecFast g;
   g.B = B; g.D = D; g.H = H; g.W = W; g.HW = H * W; g.DHW = D * H * W; g.nvox = B * D * H * W;
@@ -453,6 +460,17 @@ static int coop_grid_fast(K kernel, int threads, int* grid_out) {
   }
   *grid_out = nsm * per_sm;
   return VXM_OK;
+}
+
+extern "C" int vxm_debug_gridsync(int nsync, int ctas_per_sm, void* stream) {
+  int grid = 0;
+  int rc = coop_grid_fast(gridsync_probe_kernel, 512, &grid);
+  if (rc) return rc;
+  if (ctas_per_sm > 0 && ctas_per_sm * sm_count() < grid) grid = ctas_per_sm * sm_count();
+  unsigned* sink = nullptr;
+  void* args[] = {(void*)&nsync, (void*)&sink};
+  VXM_CUDA(cudaLaunchCooperativeKernel((void*)gridsync_probe_kernel, dim3(grid), dim3(512), args, 0, as_stream(stream)));
+  return check_launch("debug_gridsync");
 }
 
 static int vecint_fast_check(int B, int D, int H, int W, int nd, int nsteps) {

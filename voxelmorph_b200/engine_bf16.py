@@ -41,6 +41,74 @@ class _PackCache:
 _cache = _PackCache()
 
 
+class _PackPlan:
+    """Every packed operand of a model (forward + transposed copy of each convolution, swizzled kw-stacked format) refreshed
+    by ONE kernel launch (tc.vxm_conv3d_tcs_pack_multi) instead of one launch per operand (23 per training step)."""
+
+    def __init__(self, model):
+        import ctypes
+        lib = _lib.load()
+        unet = model.unet_model
+        convs = [b.main for lvl in unet.encoder for b in lvl] + [b.main for lvl in unet.decoder for b in lvl] + \
+                [b.main for b in unet.remaining] + [model.flow]
+        self.params = [c.weight for c in convs]
+        dev = self.params[0].device
+        dsz = int(lib.vxm_conv3d_tcs_pack_desc_bytes())
+        host = ctypes.create_string_buffer(dsz * 2 * len(convs))
+        self.table = {}
+        self.keep = []
+        n, begin = 0, 0
+        for li, w in enumerate(self.params):
+            w5 = w if w.dim() == 5 else w.unsqueeze(2)
+            Cout, Cin, kd = w5.shape[0], w5.shape[1], w5.shape[2]
+            for transposed in (False, True):
+                if transposed and li == 0:
+                    continue                      # the images need no gradient: no dgrad of the first layer
+                cin_eff, nout = (Cout, Cin) if transposed else (Cin, Cout)
+                if nout > 64 or cin_eff > 64:
+                    continue
+                coutp = 16 if nout <= 16 else (32 if nout <= 32 else (48 if nout <= 48 else 64))
+                nbytes = int(lib.vxm_conv3d_tcs_packed_bytes(cin_eff, coutp, kd))
+                out = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=dev)
+                cnt = lib.vxm_conv3d_tcs_pack_desc(ctypes.cast(ctypes.addressof(host) + n * dsz, ctypes.c_void_p), _lib.ptr(w), _lib.ptr(out),
+                                                   Cout, Cin, kd, coutp, 1 if transposed else 0, begin)
+                if cnt <= 0:
+                    continue
+                self.table[(id(w), transposed)] = (out, (coutp, "s"))
+                self.keep.append(out)
+                begin += cnt
+                n += 1
+        self.ndesc, self.total = n, begin
+        self.descs = torch.frombuffer(bytearray(host.raw[:max(1, n) * dsz]), dtype=torch.uint8).to(dev)
+        self.ptrs = tuple(w.data_ptr() for w in self.params)
+        self.stamp = None
+
+    def valid_for(self, model):
+        return self.ptrs == tuple(w.data_ptr() for w in self.params)
+
+    def refresh(self):
+        stamp = (_weights_epoch, tuple(w._version for w in self.params))
+        if stamp != self.stamp and self.ndesc:
+            _lib.check(_lib.load().vxm_conv3d_tcs_pack_multi(_lib.ptr(self.descs), self.ndesc, self.total, _lib.stream_ptr()),
+                       "vxm_conv3d_tcs_pack_multi")
+            self.stamp = stamp
+
+    def lookup(self, w, transposed):
+        return self.table.get((id(w), transposed))
+
+
+def _plan_of(model):
+    """The model's pack plan (built lazily; rebuilt when the parameters moved, e.g. after .to(device) or FlatParams)."""
+    if tc._variant() not in ("auto", "s"):
+        return None
+    plan = model.__dict__.get("_vxm_pack_plan")
+    if plan is None or not plan.valid_for(model):
+        plan = _PackPlan(model)
+        object.__setattr__(model, "_vxm_pack_plan", plan)
+    plan.refresh()
+    return plan
+
+
 def supports(model):
     """True when every convolution of `model` (a VxmDense) has a shape the tensor-core kernels implement: feature
     counts in {8, 16, 32}, concatenated inputs a multiple of 16 and at most 64 channels, at most 8 image planes."""
@@ -118,12 +186,13 @@ def _run_conv_split(cv, kd):
                              out_fp32_planar=cv.planar_out, slope=cv.slope)
 
 
-def _run_conv(cv, kd):
+def _run_conv(cv, kd, plan=None):
     """Forward of one tape entry."""
     ca = 0 if cv.xa is None else cv.xa.shape[-1]
     cb = 0 if cv.xb is None else cv.xb.shape[-1]
     if cv.planar is None and tc.use_t_kernel(ca, cb, cv.cout):
-        wpk, cp = _cache.get(cv.w, "fwd_t", lambda: tc.pack_weights_t(cv.w.detach()))
+        hit = plan.lookup(cv.w, False) if (plan is not None and tc._use_s(ca, cb, cv.cout)) else None
+        wpk, cp = hit if hit is not None else _cache.get(cv.w, "fwd_t", lambda: tc.pack_weights_t(cv.w.detach()))
         return tc.conv_fwd_t(cv.xa, cv.xb, wpk, cp, cv.b.detach() if cv.b is not None else None, cv.cout, kd, up=cv.up,
                              out_fp32_planar=cv.planar_out, slope=cv.slope)
     wpk, NP = _cache.get(cv.w, "fwd", lambda: tc.pack_weights(cv.w.detach()))
@@ -146,6 +215,7 @@ def forward_tape(model, source, target, split=False):
     tape = []            # list of ("conv", _Conv) / ("pool", in_id, out_id)
     tensors = {}         # id -> bf16 NDHWC tensor
     lows = {}            # id -> lo part (split precision only)
+    plan = None if split else _plan_of(model)
     producer = {}        # id -> "conv" | "pool"
     next_id = [0]
 
@@ -176,7 +246,7 @@ def forward_tape(model, source, target, split=False):
             elif ca + cb != cv.cin or (ca + cb) % 16 or ca + cb > 64:
                 raise _lib.VxmError("bf16 engine: unsupported convolution input channels %d (+%d); need a multiple of 16, at most 64"
                                     % (ca, cb))
-        out = _run_conv_split(cv, kd) if split else _run_conv(cv, kd)
+        out = _run_conv_split(cv, kd) if split else _run_conv(cv, kd, plan)
         cv.out_id = new_id()
         if split and not planar_out:
             out, lows[cv.out_id] = out
@@ -242,13 +312,14 @@ def forward_tape(model, source, target, split=False):
     flow = tape[-1][1].out
     if nd == 2:
         flow = flow.squeeze(2)
-    return flow, dict(tape=tape, tensors=tensors, producer=producer, nd=nd, kd=kd)
+    return flow, dict(tape=tape, tensors=tensors, producer=producer, nd=nd, kd=kd, plan=_plan_of(model) if split else plan)
 
 
 def backward_tape(ctx, g_flow):
     """Hand-written backward over the tape.  Returns {param: grad}."""
     lib = _lib.load()
     tape, tensors, producer, nd, kd = ctx["tape"], ctx["tensors"], ctx["producer"], ctx["nd"], ctx["kd"]
+    plan = ctx.get("plan")
     g_flow = _lib.contig(g_flow.float())
     if nd == 2:
         g_flow = g_flow.unsqueeze(2)
@@ -291,7 +362,8 @@ def backward_tape(ctx, g_flow):
             msk = tensors[t] if producer[t] == "conv" else None
             sl = _slope_of(ctx, t) if producer[t] == "conv" else None
             if tc.use_t_kernel(g_in.shape[-1], 0, cv.cin):
-                wpk, cp = _cache.get(cv.w, "dgrad_t", lambda: tc.pack_weights_t(w, transposed=True))
+                hit = plan.lookup(cv.w, True) if (plan is not None and tc._use_s(g_in.shape[-1], 0, cv.cin)) else None
+                wpk, cp = hit if hit is not None else _cache.get(cv.w, "dgrad_t", lambda: tc.pack_weights_t(w, transposed=True))
                 res = tc.conv_fwd_t(g_in, None, wpk, cp, None, cv.cin, kd, slope=sl, mask=msk)
             else:
                 wpk, NP = _cache.get(cv.w, "dgrad", lambda: tc.pack_weights(w, transposed=True))
@@ -304,7 +376,8 @@ def backward_tape(ctx, g_flow):
             ca = cv.xa.shape[-1]
             # single dgrad pass over the whole concat input: N = Ca + Cb output channels, split on store
             if tc.use_t_kernel(g_in.shape[-1], 0, cv.cin):
-                wpk, cp = _cache.get(cv.w, "dgrad_t", lambda: tc.pack_weights_t(w, transposed=True))
+                hit = plan.lookup(cv.w, True) if (plan is not None and tc._use_s(g_in.shape[-1], 0, cv.cin)) else None
+                wpk, cp = hit if hit is not None else _cache.get(cv.w, "dgrad_t", lambda: tc.pack_weights_t(w, transposed=True))
                 g_up, g_sk = tc.conv_fwd_t(g_in, None, wpk, cp, None, cv.cin, kd, split=ca)
             else:
                 wpk, NP = _cache.get(cv.w, "dgrad", lambda: tc.pack_weights(w, transposed=True))

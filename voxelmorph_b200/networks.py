@@ -162,6 +162,7 @@ class VxmDense(LoadableModel):
         self.training = True
         object.__setattr__(self, "_dp", None)            # dist.TransparentDP once attached (not a submodule / buffer)
         object.__setattr__(self, "_dp_checked", False)
+        self.registration_no_grad = True     # eval-mode registration calls run without autograd bookkeeping (see forward)
         ndims = len(inshape)
         assert ndims in [1, 2, 3], 'ndims should be one of 1, 2, or 3. found: %d' % ndims
 
@@ -205,8 +206,10 @@ class VxmDense(LoadableModel):
             return                       # one checkpoint per job: rank 0 writes
         super().save(path)
 
-    def forward(self, source, target, registration=False):
-        self._maybe_attach_dp()
+    def flows(self, source, target):
+        """(pos_flow, neg_flow, preint_flow): the U-Net's field brought to the integration resolution (`preint_flow`,
+        what train.py regularises), integrated and brought back to full resolution (`pos_flow`, what warps the moving
+        image; `neg_flow` its inverse when bidir).  reference networks.py:253-276."""
         engine = ops.resolve_engine(self)
         if engine in ('bf16', 'bf16x3'):
             # tensor-core engine: Unet + flow head as one hand-written forward/backward (engine_bf16.py)
@@ -229,10 +232,81 @@ class VxmDense(LoadableModel):
             if self.fullsize:
                 pos_flow = self.fullsize(pos_flow)
                 neg_flow = self.fullsize(neg_flow) if self.bidir else None
+        return pos_flow, neg_flow, preint_flow
 
+    def forward(self, source, target, registration=False):
+        self._maybe_attach_dp()
+        if registration and not self.training and self.registration_no_grad and torch.is_grad_enabled():
+            # inference (register.py:80-87 calls model.eval() but never torch.no_grad()): nothing downstream of a
+            # registration call differentiates, so no activation / VecInt state is kept ("next" row N3)
+            with torch.no_grad():
+                return self.forward(source, target, registration=True)
+        pos_flow, neg_flow, preint_flow = self.flows(source, target)
         y_source = self.transformer(source, pos_flow)
         y_target = self.transformer(target, neg_flow) if self.bidir else None
 
         if not registration:
             return (y_source, y_target, preint_flow) if self.bidir else (y_source, preint_flow)
         return y_source, pos_flow
+
+
+class VxmDenseSemiSupervisedSeg(LoadableModel):
+    """VoxelMorph network for semi-supervised registration with segmentations ("next" row N2; BASELINE config 5).
+
+    The torch backend of the reference has no such class; the semantics are those of its TensorFlow model
+    (voxelmorph/tf/networks.py:287-366) restated over the torch layers, as SURVEY.md section 8(a) A12 specifies: the
+    full-resolution `pos_flow` of the inner VxmDense is rescaled to the segmentation resolution
+    (`ResizeTransform(seg_resolution)`, i.e. RescaleTransform(1 / seg_resolution)), the probabilistic (one-hot) source
+    segmentation is warped LINEARLY with it, and the result joins the outputs so that a Dice loss can be attached:
+
+        y_source, preint_flow, y_seg = model(source, target, seg_source)
+        loss = image_loss(target, y_source) + w_grad * Grad(preint_flow) + w_seg * Dice(seg_target, y_seg)
+
+    `bidir_labels` additionally warps the target segmentation with `neg_flow` (and implies bidir).  The inner network is
+    `self.vxm_model` (checkpoint keys `vxm_model.*`); `kwargs` are forwarded to it."""
+
+    @store_config_args
+    def __init__(self, inshape, nb_labels, nb_unet_features=None, seg_resolution=2, bidir=False, bidir_labels=False, **kwargs):
+        super().__init__()
+        if bidir_labels:
+            bidir = True
+        ndims = len(inshape)
+        self.nb_labels = int(nb_labels)
+        self.bidir_labels = bool(bidir_labels)
+        self.vxm_model = VxmDense(inshape, nb_unet_features=nb_unet_features, bidir=bidir, **kwargs)
+        self.seg_resize = layers.ResizeTransform(seg_resolution, ndims) if seg_resolution != 1 else None
+        inshape_ds = [int(d / seg_resolution) for d in inshape]
+        self.seg_transformer = layers.SpatialTransformer(inshape_ds)        # linear: the segmentation is a probability map
+
+    def forward(self, source, target, seg_source, seg_target=None, registration=False):
+        vm = self.vxm_model
+        vm._maybe_attach_dp()
+        pos_flow, neg_flow, preint_flow = vm.flows(source, target)
+        y_source = vm.transformer(source, pos_flow)
+        y_target = vm.transformer(target, neg_flow) if vm.bidir else None
+        seg_flow = self.seg_resize(pos_flow) if self.seg_resize else pos_flow
+        y_seg = self.seg_transformer(seg_source, seg_flow)
+        outs = [y_source] + ([y_target] if vm.bidir else []) + [pos_flow if registration else preint_flow, y_seg]
+        if self.bidir_labels:
+            if seg_target is None:
+                raise ValueError("bidir_labels=True needs the target segmentation")
+            nseg_flow = self.seg_resize(neg_flow) if self.seg_resize else neg_flow
+            outs.append(self.seg_transformer(seg_target, nseg_flow))
+        return tuple(outs)
+
+    def save(self, path):
+        dp = self.vxm_model._dp
+        if dp is not None and not dp.is_writer():
+            return
+        super().save(path)
+
+    def register(self, source, target):
+        """The transform from source to target (full resolution), like tf get_registration_model / register."""
+        with torch.no_grad():
+            return self.vxm_model.flows(source, target)[0]
+
+    def apply_transform(self, source, target, img, interp_method='linear'):
+        """Predict the transform from source to target and apply it to `img` ('linear' or 'nearest')."""
+        mode = 'bilinear' if interp_method == 'linear' else interp_method
+        flow = self.register(source, target)
+        return layers.SpatialTransformer(tuple(img.shape[2:]), mode=mode)(img, flow)

@@ -164,9 +164,10 @@ def _use_s(ca, cb, cout):
 
 
 def _use_s2(xa, xb, coutp, full, up, kd):
-    """VXM_B200_TCS2=1: the two-issuer variant wherever the one-issuer kernel would pick 8-row tiles."""
+    """The two-issuer variant (conv3d_tc_s2.cu) wherever the one-issuer kernel would pick 8-row tiles; VXM_B200_TCS2=0
+    switches back to the single issuer (A/B)."""
     import os
-    if os.environ.get("VXM_B200_TCS2", "0") != "1":
+    if os.environ.get("VXM_B200_TCS2", "1") != "1":      # default on: +5 % step throughput on B200 (profiles/r2_tcs2_ab.md)
         return False
     cin = (0 if xa is None else xa.shape[-1]) + (0 if xb is None else xb.shape[-1])
     H = full.shape[2] * (2 if (xb is None and up) else 1)

@@ -71,9 +71,31 @@ def jacobian_determinant(disp):
             + dx[..., 2] * (dy[..., 0] * dz[..., 1] - dy[..., 1] * dz[..., 0]))
 
 
+def jacobian_determinant_device(flow, return_folds=False):
+    """det J on the GPU for a CUDA tensor in the module layout (B, nb_dims, *vol) — the warp `VxmDense(..., registration=True)`
+    returns — with np.gradient's differencing and the reference's determinant expansion (py/utils.py:473-516).  Returns a
+    (B, *vol) tensor, plus the number of folded voxels (det <= 0, python int) when `return_folds`."""
+    import torch
+    from . import _lib
+    from .layers import _dims
+    _lib.require_cuda(flow, what="jacobian_determinant_device")
+    flow = _lib.contig(flow.detach())
+    B, C, D, H, W, nd = _dims(flow)
+    if C != nd:
+        raise _lib.VxmError("jacobian_determinant_device: expected %d displacement channels, got %d" % (nd, C))
+    det = torch.empty((B,) + tuple(flow.shape[2:]), dtype=torch.float32, device=flow.device)
+    folds = torch.zeros(1, dtype=torch.int64, device=flow.device) if return_folds else None
+    _lib.check(_lib.load().vxm_jacdet(_lib.ptr(flow), _lib.ptr(det), _lib.ptr(folds), B, D, H, W, nd, _lib.stream_ptr()), "vxm_jacdet")
+    return (det, int(folds.item())) if return_folds else det
+
+
 def count_folds(flow):
     """Number of voxels where the deformation folds (det J <= 0).  `flow`: module-layout field (nb_dims, *vol) or
-    (1, nb_dims, *vol) as `VxmDense(..., registration=True)` returns it (numpy array or CPU tensor)."""
+    (1, nb_dims, *vol) as `VxmDense(..., registration=True)` returns it.  CUDA tensors are evaluated on the device
+    (csrc/eval_ops.cu), numpy arrays / CPU tensors on the host."""
+    if hasattr(flow, "is_cuda") and flow.is_cuda:
+        f = flow if flow.dim() in (4, 5) and flow.shape[1] == flow.dim() - 2 else flow.unsqueeze(0)
+        return jacobian_determinant_device(f, return_folds=True)[1]
     f = np.asarray(flow.detach().cpu() if hasattr(flow, "detach") else flow, dtype=np.float64)
     if f.ndim in (4, 5) and f.shape[0] == 1 and f.shape[1] == f.ndim - 2:
         f = f[0]
