@@ -224,6 +224,18 @@ int vxm_conv3d_tc_wgrad(const void* xa, const void* xb, const float* const* xf, 
                         int nplanar_x, const void* gz, const float* const* gf, const long long* gf_bstride,
                         int nplanar_g, float* grad_w, float* grad_b, void* work, int B, int D, int H, int W,
                         int Ca, int Cb, int up, int Cin_real, int Cg, int Cout_real, int kd, int accumulate, void* stream);
+/* Deferred reduction of the weight gradient (channels-last bf16 sources only): `_partial` launches the tcgen05 kernel(s) of
+ * one layer into caller-provided workspace (`work_used` bytes of it are then owned by this layer until the flush) and
+ * appends the pending reductions to a HOST array of descriptors (vxm_conv3d_tc_wgrad2_desc_bytes() each, at most
+ * vxm_conv3d_tc_wgrad2_max_pending()); `_flush` reduces every pending layer in ONE launch, in a fixed order
+ * (deterministic).  Arguments as vxm_conv3d_tc_wgrad. */
+size_t vxm_conv3d_tc_wgrad2_desc_bytes(void);
+int vxm_conv3d_tc_wgrad2_max_pending(void);
+size_t vxm_conv3d_tc_wgrad2_partial_bytes(int kd);
+int vxm_conv3d_tc_wgrad2_partial(const void* xa, const void* xb, const void* gz, float* grad_w, float* grad_b, void* work,
+                                 size_t work_bytes, size_t* work_used, void* descs_host, int* ndesc, int B, int D, int H, int W,
+                                 int Ca, int Cb, int up, int Cin_real, int Cg, int Cout_real, int kd, int accumulate, void* stream);
+int vxm_conv3d_tc_wgrad2_flush(const void* descs_host, int ndesc, void* stream);
 /* ---- channels-last bf16 glue of the tensor-core U-Net engine (reference networks.py:126-138 and its autograd) ----
  * All tensors bf16 (B,D,H,W,C), C % 8 == 0.  (Dc,Hc,Wc) are the COARSE dims; the fine tensor is (fd*Dc, 2Hc, 2Wc)
  * with fd = 2 for nd == 3 and 1 for nd == 2. */

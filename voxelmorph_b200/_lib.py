@@ -65,6 +65,11 @@ SIGNATURES = {
     "vxm_conv3d_tcs_fwd_acc": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_f] + [c_i] * 11 + [c_fl, c_f]),
     "vxm_conv3d_tc_wgrad_workspace_bytes": (c_sz, [c_i]),
     "vxm_conv3d_tc_wgrad": (c_i, [c_f, c_f, c_f, c_f, c_i, c_f, c_f, c_f, c_i, c_f, c_f, c_f] + [c_i] * 12 + [c_f]),
+    "vxm_conv3d_tc_wgrad2_desc_bytes": (c_sz, []),
+    "vxm_conv3d_tc_wgrad2_max_pending": (c_i, []),
+    "vxm_conv3d_tc_wgrad2_partial_bytes": (c_sz, [c_i]),
+    "vxm_conv3d_tc_wgrad2_partial": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_sz, c_f, c_f, c_f] + [c_i] * 12 + [c_f]),
+    "vxm_conv3d_tc_wgrad2_flush": (c_i, [c_f, c_i, c_f]),
     "vxm_pool2_ndhwc_bf16": (c_i, [c_f, c_f] + [c_i] * 6 + [c_f]),
     "vxm_sumpool_mask_ndhwc_bf16": (c_i, [c_f, c_f, c_f] + [c_i] * 6 + [c_fl, c_f]),
     "vxm_unpool_combine_ndhwc_bf16": (c_i, [c_f, c_f, c_f, c_f] + [c_i] * 6 + [c_fl, c_f]),

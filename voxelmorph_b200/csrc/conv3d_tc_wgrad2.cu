@@ -374,6 +374,48 @@ __global__ void __launch_bounds__(256) wgrad2_reduce_kernel(const float* __restr
   }
 }
 
+// All reductions of a backward pass in ONE launch (16 reduce launches per training step otherwise).  The descriptors
+// travel by value in the kernel parameters (no device table to keep alive or re-upload inside a captured graph).
+struct ReduceDesc {
+  const float* partial; float* gw; const float* bias_partial; float* gb;
+  int ncta, T, G, GOUT, Cout, Cin_total, ci_off, ci_cnt, accumulate, blk_begin;
+};
+constexpr int MAXRED = 40;
+struct ReduceBatch {
+  ReduceDesc d[MAXRED];
+  int n, total_blocks;
+};
+__global__ void __launch_bounds__(256) wgrad2_reduce_multi_kernel(const ReduceBatch rb) {
+  __shared__ float sh[4][64];
+  int k = 0;
+  for (int i = 1; i < rb.n; ++i)
+    if ((int)blockIdx.x >= rb.d[i].blk_begin) k = i;
+  const ReduceDesc& r = rb.d[k];
+  const int blk = blockIdx.x - r.blk_begin;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  if (r.gb && blk == 0 && threadIdx.x < r.Cout) {
+    float acc = r.accumulate ? r.gb[threadIdx.x] : 0.f;
+    for (int c = 0; c < r.ncta; ++c) acc += r.bias_partial[(size_t)c * r.GOUT + threadIdx.x];
+    r.gb[threadIdx.x] = acc;
+  }
+  const int per_cta = r.T * r.G * r.GOUT;
+  const int j = blk * 64 + tx;
+  const int q = (r.ncta + 3) / 4, c0 = ty * q, c1 = min(c0 + q, r.ncta);
+  float acc = 0.f;
+  if (j < per_cta)
+    for (int c = c0; c < c1; ++c) acc += r.partial[(size_t)c * per_cta + j];
+  sh[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && j < per_cta) {
+    const int co = j % r.GOUT, ci = (j / r.GOUT) % r.G, tap = j / (r.GOUT * r.G);
+    if (co < r.Cout && ci < r.ci_cnt) {
+      const float tot = ((sh[0][tx] + sh[1][tx]) + sh[2][tx]) + sh[3][tx];
+      float* dst = r.gw + ((size_t)co * r.Cin_total + r.ci_off + ci) * r.T + tap;
+      *dst = (r.accumulate ? *dst : 0.f) + tot;
+    }
+  }
+}
+
 }  // namespace tcw
 }  // namespace vxm
 
@@ -393,7 +435,8 @@ bool wgrad2_supported(int Ca, int Cb, int Cg) {
 
 // one source tensor (C channels, optionally nearest-x2 upsampled) against gz; weights [ci_off, ci_off + ci_cnt) of Cin_total
 int wgrad2_launch(const void* x, int Cx, int up, const void* gz, int Cg, float* grad_w, float* grad_b, void* work, int B, int D, int H, int W,
-                  int kd, int Cout_real, int Cin_total, int ci_off, int ci_cnt, int accumulate, cudaStream_t st) {
+                  int kd, int Cout_real, int Cin_total, int ci_off, int ci_cnt, int accumulate, cudaStream_t st, ReduceDesc* defer,
+                  size_t* work_used) {
   Wgrad2Args a{};
   a.x = (const __nv_bfloat16*)x; a.Cx = Cx; a.up = up; a.upd = (up && kd == 3) ? 1 : 0;
   a.gz = (const __nv_bfloat16*)gz; a.Cg = Cg;
@@ -417,7 +460,15 @@ int wgrad2_launch(const void* x, int Cx, int up, const void* gz, int Cg, float* 
   int grid = a.nitems < nsm ? a.nitems : nsm;
   if (grid > 256) grid = 256;
   a.partial = (float*)work;
-  a.bias_partial = grad_b ? (float*)work + (size_t)256 * kd * 9 * 64 * 32 : nullptr;
+  if (defer) {
+    // deferred reduction: this launch owns exactly [work, work + *work_used): partials, then bias partials
+    const size_t npart = (size_t)grid * kd * 9 * G * GOUT;
+    a.bias_partial = grad_b ? (float*)work + npart : nullptr;
+    *work_used = (npart + (grad_b ? (size_t)grid * GOUT : 0)) * sizeof(float);
+    *work_used = (*work_used + 255) & ~(size_t)255;
+  } else {
+    a.bias_partial = grad_b ? (float*)work + (size_t)256 * kd * 9 * 64 * 32 : nullptr;
+  }
   const size_t xslab = (size_t)XROWS * 2 * G, gslab = (size_t)GSROWS * 2 * GOUT;
   const int extra = kd == 3 ? 3 : 0;
   int nslot = (int)((200 * 1024 - NGS * gslab - 512) / xslab) - extra;
@@ -439,6 +490,12 @@ int wgrad2_launch(const void* x, int Cx, int up, const void* gz, int Cg, float* 
   int rc = check_launch("conv3d_tc_wgrad2");
   if (rc) return rc;
   const int T = kd * 9, per_cta = T * G * GOUT;
+  if (defer) {
+    defer->partial = a.partial; defer->gw = grad_w; defer->bias_partial = a.bias_partial; defer->gb = grad_b;
+    defer->ncta = grid; defer->T = T; defer->G = G; defer->GOUT = GOUT; defer->Cout = Cout_real; defer->Cin_total = Cin_total;
+    defer->ci_off = ci_off; defer->ci_cnt = ci_cnt; defer->accumulate = accumulate; defer->blk_begin = (per_cta + 63) / 64;   // block count, turned into an offset by the flush
+    return VXM_OK;
+  }
   wgrad2_reduce_kernel<<<(per_cta + 63) / 64, 256, 0, st>>>(a.partial, grad_w, grid, T, G, GOUT, Cout_real, Cin_total, ci_off, ci_cnt,
                                                               a.bias_partial, grad_b, accumulate);
   return check_launch("conv3d_tc_wgrad2_reduce");
@@ -446,3 +503,62 @@ int wgrad2_launch(const void* x, int Cx, int up, const void* gz, int Cg, float* 
 
 }  // namespace tcw
 }  // namespace vxm
+
+// ---- deferred reduction API -------------------------------------------------------------------------------------------
+// vxm_conv3d_tc_wgrad2_partial launches the weight-gradient kernel(s) of one layer into caller-provided workspace and
+// appends the pending reductions to a HOST descriptor buffer; vxm_conv3d_tc_wgrad2_flush then runs every pending
+// reduction of the backward pass in one launch (fixed summation order -> deterministic, as before).
+extern "C" size_t vxm_conv3d_tc_wgrad2_desc_bytes(void) { return sizeof(ReduceDesc); }
+extern "C" int vxm_conv3d_tc_wgrad2_max_pending(void) { return MAXRED; }
+extern "C" size_t vxm_conv3d_tc_wgrad2_partial_bytes(int kd) {
+  // upper bound for one layer (two sources): 2 x 256 CTAs x 27 x 32 x 32 floats + bias partials
+  return 2 * ((size_t)256 * kd * 9 * 32 * 32 + 256 * 32) * sizeof(float) + 1024;
+}
+
+extern "C" int vxm_conv3d_tc_wgrad2_partial(const void* xa, const void* xb, const void* gz, float* grad_w, float* grad_b, void* work,
+                                            size_t work_bytes, size_t* work_used, void* descs_host, int* ndesc, int B, int D, int H, int W,
+                                            int Ca, int Cb, int up, int Cin_real, int Cg, int Cout_real, int kd, int accumulate, void* stream) {
+  VXM_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && grad_w && work && work_used && descs_host && ndesc && gz, "conv3d_tc_wgrad2_partial: bad argument");
+  VXM_REQUIRE(kd == 1 || kd == 3, "conv3d_tc_wgrad2_partial: kd must be 1 or 3");
+  VXM_REQUIRE(wgrad2_supported(Ca, Cb, Cg), "conv3d_tc_wgrad2_partial: channel counts (%d,%d | %d) unsupported", Ca, Cb, Cg);
+  VXM_REQUIRE((Ca == 0 || xa) && (Cb == 0 || xb), "conv3d_tc_wgrad2_partial: missing source tensor");
+  VXM_REQUIRE(*ndesc + 2 <= MAXRED, "conv3d_tc_wgrad2_partial: too many pending reductions (flush first)");
+  VXM_REQUIRE(Cout_real > 0 && Cout_real <= Cg, "conv3d_tc_wgrad2_partial: Cout_real out of range");
+  ReduceDesc* d = (ReduceDesc*)descs_host;
+  cudaStream_t st = as_stream(stream);
+  size_t used = 0, total = 0;
+  char* wp = (char*)work;
+  if (Ca) {
+    const int cnt = Cin_real < Ca ? Cin_real : Ca;
+    int rc = wgrad2_launch(xa, Ca, up, gz, Cg, grad_w, grad_b, wp, B, D, H, W, kd, Cout_real, Cin_real, 0, cnt, accumulate, st, &d[*ndesc], &used);
+    if (rc) return rc;
+    VXM_REQUIRE(used <= work_bytes, "conv3d_tc_wgrad2_partial: workspace too small");
+    ++*ndesc; wp += used; total += used;
+  }
+  if (Cb && Cin_real > Ca) {
+    const int cnt = Cin_real - Ca < Cb ? Cin_real - Ca : Cb;
+    int rc = wgrad2_launch(xb, Cb, 0, gz, Cg, grad_w, Ca ? nullptr : grad_b, wp, B, D, H, W, kd, Cout_real, Cin_real, Ca, cnt, accumulate, st,
+                           &d[*ndesc], &used);
+    if (rc) return rc;
+    VXM_REQUIRE(total + used <= work_bytes, "conv3d_tc_wgrad2_partial: workspace too small");
+    ++*ndesc; total += used;
+  }
+  *work_used = total;
+  return VXM_OK;
+}
+
+extern "C" int vxm_conv3d_tc_wgrad2_flush(const void* descs_host, int ndesc, void* stream) {
+  VXM_REQUIRE(descs_host && ndesc > 0 && ndesc <= MAXRED, "conv3d_tc_wgrad2_flush: bad argument");
+  ReduceBatch rb;
+  const ReduceDesc* d = (const ReduceDesc*)descs_host;
+  int blocks = 0;
+  for (int i = 0; i < ndesc; ++i) {
+    rb.d[i] = d[i];
+    const int nb = d[i].blk_begin;      // wgrad2_launch stored the block count here
+    rb.d[i].blk_begin = blocks;
+    blocks += nb;
+  }
+  rb.n = ndesc; rb.total_blocks = blocks;
+  wgrad2_reduce_multi_kernel<<<blocks, 256, 0, as_stream(stream)>>>(rb);
+  return check_launch("conv3d_tc_wgrad2_reduce_multi");
+}

@@ -229,6 +229,107 @@ __global__ void __launch_bounds__(256) resize_bwd_march_kernel(const float* __re
   while (zcur < iz_end) flush();
 }
 
+// Tiled adjoint for upsampling ratios (the backward of `fullsize`, reading the FULL-resolution gradient): the marching
+// kernel's lanes read that gradient with stride ~2 (~3 L1 wavefronts per load, 16-25 loads per plane and channel) and are
+// bound by L1 wavefronts (143 us at 160x192x224).  Here a CTA stages the output-gradient region its 4 x 8 x 32 input tile
+// touches in shared memory with coalesced row loads, then applies the three 1-D adjoints separably in shared memory
+// (x: lane = input column with its list in registers; y: warp = input row; z: 4 slices), ~45 shared loads per result.
+constexpr int RT_X = 32, RT_Y = 8, RT_Z = 4, RT_MX = 72, RT_MY = 22, RT_MZ = 12;
+constexpr size_t RT_SMEM = (size_t)(RT_MZ * RT_MY * RT_MX + RT_MZ * RT_MY * RT_X) * sizeof(float);
+
+__device__ __forceinline__ float adj_dot(const AdjList& L, const float* __restrict__ p, int stride) {
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < ADJ_L; ++k)
+    if (k < L.n) acc += L.w[k] * p[k * stride];
+  return acc;
+}
+
+__global__ void __launch_bounds__(256, 2) resize_bwd_tile_kernel(const float* __restrict__ gout, float* __restrict__ gx, ResizeGeom g, int nzt) {
+  extern __shared__ __align__(16) float rsm[];
+  float* G = rsm;                                   // [EZ][EY][RT_MX]  staged output gradient
+  float* X1 = rsm + RT_MZ * RT_MY * RT_MX;          // [EZ][EY][32]     after the x adjoint
+  float* Y1 = rsm;                                  // [EZ][8][32]      after the y adjoint (reuses G)
+  __shared__ AdjList ends[6];                       // first / last list of the tile along x, y, z
+  __shared__ AdjList zl[RT_Z];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int bx = blockIdx.x * RT_X, by = blockIdx.y * RT_Y;
+  const int bz = (blockIdx.z % nzt) * RT_Z, bc = blockIdx.z / nzt;
+  if (tid < 6) {
+    const AxisMap& m = tid < 2 ? g.mx : (tid < 4 ? g.my : g.mz);
+    const int b0 = tid < 2 ? bx : (tid < 4 ? by : bz), T = tid < 2 ? RT_X : (tid < 4 ? RT_Y : RT_Z);
+    make_adj(m, (tid & 1) ? min(b0 + T - 1, m.in - 1) : b0, ends[tid]);
+  } else if (tid >= 32 && tid < 32 + RT_Z) {
+    const int iz = bz + (tid - 32);
+    if (iz < g.mz.in) make_adj(g.mz, iz, zl[tid - 32]); else zl[tid - 32].n = 0;
+  }
+  __syncthreads();
+  const int xlo = ends[0].lo, ylo = ends[2].lo, zlo = ends[4].lo;
+  const int EX = min(ends[1].lo + ends[1].n - xlo, RT_MX), EY = min(ends[3].lo + ends[3].n - ylo, RT_MY), EZ = min(ends[5].lo + ends[5].n - zlo, RT_MZ);
+  const size_t oHW = (size_t)g.my.out * g.mx.out, cout = oHW * g.mz.out;
+  const float* gb = gout + (size_t)bc * cout + (size_t)zlo * oHW + (size_t)ylo * g.mx.out + xlo;
+  for (int row = warp; row < EZ * EY; row += 8) {
+    const int z = row / EY, y = row - z * EY;
+    const float* src = gb + (size_t)z * oHW + (size_t)y * g.mx.out;
+    float* dst = G + (z * RT_MY + y) * RT_MX;
+    for (int x = lane; x < EX; x += 32) dst[x] = __ldg(src + x);
+  }
+  __syncthreads();
+  const int ix = bx + lane, iy = by + warp;
+  {
+    AdjList X;
+    if (ix < g.mx.in) make_adj(g.mx, ix, X); else { X.lo = xlo; X.n = 0; }
+    const int xo = X.lo - xlo;
+    for (int row = warp; row < EZ * EY; row += 8) {
+      const int z = row / EY, y = row - z * EY;
+      X1[(z * RT_MY + y) * RT_X + lane] = adj_dot(X, G + (z * RT_MY + y) * RT_MX + xo, 1);
+    }
+  }
+  __syncthreads();
+  {
+    AdjList Y;
+    if (iy < g.my.in) make_adj(g.my, iy, Y); else { Y.lo = ylo; Y.n = 0; }
+    const int yo = Y.lo - ylo;
+    for (int z = 0; z < EZ; ++z) Y1[(z * RT_Y + warp) * RT_X + lane] = adj_dot(Y, X1 + (z * RT_MY + yo) * RT_X + lane, RT_X);
+  }
+  __syncthreads();
+  if (ix < g.mx.in && iy < g.my.in) {
+    float* ob = gx + (((size_t)bc * g.mz.in + bz) * g.my.in + iy) * g.mx.in + ix;
+#pragma unroll
+    for (int j = 0; j < RT_Z; ++j) {
+      if (bz + j < g.mz.in) {
+        const AdjList& Z = zl[j];
+        ob[(size_t)j * g.my.in * g.mx.in] = adj_dot(Z, Y1 + ((Z.lo - zlo) * RT_Y + warp) * RT_X + lane, RT_Y * RT_X) * g.scale;
+      }
+    }
+  }
+}
+
+// largest number of outputs any T-wide input tile touches along one axis (same fp32 index arithmetic as the device)
+static int host_tile_extent(const AxisMap& m, int T) {
+  if (m.in == m.out) return T;
+  int worst = 0;
+  const int ntile = (m.in + T - 1) / T;
+  int o = 0;
+  for (int t = 0; t < ntile; ++t) {
+    const int b0 = t * T, b1 = (b0 + T - 1 < m.in - 1) ? b0 + T - 1 : m.in - 1;
+    int first = -1, last = -1;
+    // outputs are monotone in their source index: walk from a little before the previous tile's end
+    for (int q = (o > 4 ? o - 4 : 0); q < m.out; ++q) {
+      const float real = m.ratio * (float)q;
+      int i0 = (int)real;
+      if (i0 > m.in - 1) i0 = m.in - 1;
+      const int i1 = i0 + (i0 < m.in - 1 ? 1 : 0);
+      if (i1 < b0) continue;
+      if (i0 > b1) break;
+      if (first < 0) first = q;
+      last = q;
+    }
+    if (first >= 0) { if (last - first + 1 > worst) worst = last - first + 1; o = last; }
+  }
+  return worst;
+}
+
 // generic fallback (any ratio): one thread per input voxel, weights recomputed in the loops
 __global__ void __launch_bounds__(256) resize_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gx, ResizeGeom g) {
   int ix = blockIdx.x * 32 + threadIdx.x;
@@ -296,7 +397,16 @@ extern "C" int vxm_resize_bwd(const float* grad_out, float* grad_x, int B, int C
   cudaStream_t st = as_stream(stream);
   // an input index is touched by at most ~2/ratio + 1 outputs; the marching kernel keeps ADJ_L of them in registers
   auto fits = [](const AxisMap& m) { return m.in == m.out || (m.ratio > 0.f && 2.0f / m.ratio + 1.5f <= (float)ADJ_L); };
-  if (fits(g.mz) && fits(g.my) && fits(g.mx)) {
+  const char* ek = getenv("VXM_B200_RESIZE_BWD");      // "march": A/B switch
+  const bool up = Do > Di && Ho > Hi && Wo > Wi && !(ek && ek[0] == 'm');
+  if (up && fits(g.mz) && fits(g.my) && fits(g.mx) && host_tile_extent(g.mx, RT_X) <= RT_MX && host_tile_extent(g.my, RT_Y) <= RT_MY &&
+      host_tile_extent(g.mz, RT_Z) <= RT_MZ) {
+    const int nzt = (Di + RT_Z - 1) / RT_Z;
+    VXM_REQUIRE((size_t)nzt * B * C <= 65535u, "resize_bwd: B*C*D exceeds the launch grid limit");
+    VXM_CUDA(cudaFuncSetAttribute(resize_bwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM));
+    dim3 grid((Wi + RT_X - 1) / RT_X, (Hi + RT_Y - 1) / RT_Y, nzt * B * C);
+    resize_bwd_tile_kernel<<<grid, 256, RT_SMEM, st>>>(grad_out, grad_x, g, nzt);
+  } else if (fits(g.mz) && fits(g.my) && fits(g.mx)) {
     const int nc = channels_per_thread(B * C);
     dim3 block(32, 8, 1), grid((Wi + 31) / 32, (Hi + 7) / 8, g.nzc * (B * C / nc));
     if (nc == 3) resize_bwd_march_kernel<3><<<grid, block, 0, st>>>(grad_out, grad_x, g);

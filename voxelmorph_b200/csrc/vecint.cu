@@ -262,15 +262,19 @@ __global__ void __launch_bounds__(512) vecint_fwd_fast_kernel(const float* __res
   }
   grid.sync();
   for (int s = 0; s < nsteps; ++s) {
-    const float4* cur = field(s);
-    float4* nxt = field(s + 1);
+    const float4* __restrict__ cur = field(s);
+    float4* __restrict__ nxt = field(s + 1);
     const bool last = s + 1 == nsteps;
+    // the voxel's own vector of the NEXT iteration is requested before this iteration's gathers: the dependent chain of an
+    // iteration is then one L2 round trip (the gathers), not two (own value -> coordinates -> gathers)
+    float4 v_next = tid0 < g.nvox ? cur[tid0] : make_float4(0.f, 0.f, 0.f, 0.f);
     for (int q = tid0; q < g.nvox; q += stride) {
       const int t1 = fdiv(q, g.dW), x = q - t1 * g.W;
       const int t2 = fdiv(t1, g.dH), y = t1 - t2 * g.H;
       const int b = fdiv(t2, g.dD), z = t2 - b * g.D;
       const float4* cb = cur + (size_t)b * g.DHW;
-      const float4 v = cur[q];
+      const float4 v = v_next;
+      if (q + stride < g.nvox) v_next = cur[q + stride];
       Corner8 c;
       corners_fast((float)z + v.x, (float)y + v.y, (float)x + v.z, g, c);
       float4 r;
@@ -321,18 +325,21 @@ __global__ void __launch_bounds__(512) vecint_bwd_fast_kernel(const float* __res
   grid.sync();
   for (int j = 0; j < nsteps; ++j) {
     const int k = nsteps - 1 - j;
-    const float4* v = states + (size_t)k * g.nvox;
-    const float4* gn = j % 3 == 0 ? G0 : (j % 3 == 1 ? G1 : G2);
+    const float4* __restrict__ v = states + (size_t)k * g.nvox;
+    const float4* __restrict__ gn = j % 3 == 0 ? G0 : (j % 3 == 1 ? G1 : G2);
     float4* gc = j % 3 == 0 ? G1 : (j % 3 == 1 ? G2 : G0);
-    float4* gz = j % 3 == 0 ? G2 : (j % 3 == 1 ? G0 : G1);
+    float4* __restrict__ gz = j % 3 == 0 ? G2 : (j % 3 == 1 ? G0 : G1);
+    float4 own_next = make_float4(0.f, 0.f, 0.f, 0.f), go_next = own_next;
+    if (tid0 < g.nvox) { own_next = v[tid0]; go_next = gn[tid0]; }
     for (int q = tid0; q < g.nvox; q += stride) {
       const int t1 = fdiv(q, g.dW), x = q - t1 * g.W;
       const int t2 = fdiv(t1, g.dH), y = t1 - t2 * g.H;
       const int b = fdiv(t2, g.dD), z = t2 - b * g.D;
       const float4* vb = v + (size_t)b * g.DHW;
       float4* gcb = gc + (size_t)b * g.DHW;
-      const float4 own = v[q];
-      const float4 go = gn[q];
+      const float4 own = own_next;
+      const float4 go = go_next;
+      if (q + stride < g.nvox) { own_next = v[q + stride]; go_next = gn[q + stride]; }   // next iteration's own data, ahead of this one's gathers
       gz[q] = make_float4(0.f, 0.f, 0.f, 0.f);
       Corner8 c;
       corners_fast((float)z + own.x, (float)y + own.y, (float)x + own.z, g, c);

@@ -157,7 +157,7 @@ __device__ __forceinline__ float blend_fast(const float* __restrict__ plane, boo
   return sample8<IS3D, true>(plane, st);
 }
 
-template <bool IS3D>
+template <bool IS3D, bool C1>
 __global__ void __launch_bounds__(TX* TY) warp_fwd_fast_kernel(const float* __restrict__ src, const float* __restrict__ flow,
                                                                float* __restrict__ out, FastGeom g) {
   const int x = blockIdx.x * TX + threadIdx.x;
@@ -195,15 +195,34 @@ __global__ void __launch_bounds__(TX* TY) warp_fwd_fast_kernel(const float* __re
     if (!interior) make_stencil8<IS3D>(cx, cy, cz, g.Ds, g.Hs, g.Ws, st);
     const int base = (zz0 * g.Hs + y0) * g.Ws + x0;
     const float tx = cx - fx, ty = cy - fy, tz = cz - fz;
-    for (int c = 0; c < g.C; ++c)
-      ob[(size_t)c * DHW + z * HW] = blend_fast<IS3D>(sb + (size_t)c * sDHW, interior, base, sW, sHW, tx, ty, tz, st);
+    if (C1) {
+      ob[z * HW] = blend_fast<IS3D>(sb, interior, base, sW, sHW, tx, ty, tz, st);
+    } else {
+      for (int c = 0; c < g.C; ++c)
+        ob[(size_t)c * DHW + z * HW] = blend_fast<IS3D>(sb + (size_t)c * sDHW, interior, base, sW, sHW, tx, ty, tz, st);
+    }
   }
 }
 
 // backward of the fast path: d out / d flow from the same lerp tree (needs the 8 corner values once per channel),
-// d out / d src as a scatter (red.global.add) only when the caller asks for it.
+// d out / d src as a scatter (red.global.add) only when the caller asks for it.  NOSRC: no gradient w.r.t. the source
+// (the moving image of the training step) — with interior voxels on a predicate-free branch this is the variant the
+// step runs; the general form handles borders, source gradients and several channels.
 template <bool IS3D>
-__global__ void __launch_bounds__(TX* TY) warp_bwd_fast_kernel(const float* __restrict__ gout, const float* __restrict__ src,
+__device__ __forceinline__ void dflow_from_corners(float a00, float a01, float a10, float a11, float b00, float b01, float b10, float b11,
+                                                   float tx, float ty, float tz, float go, float& gx, float& gy, float& gz) {
+  // d/dx: lerp_z(lerp_y(b - a along x));  d/dy, d/dz alike
+  const float dxa = fmaf(ty, (a11 - a10) - (a01 - a00), a01 - a00), dxb = fmaf(ty, (b11 - b10) - (b01 - b00), b01 - b00);
+  const float ra0 = fmaf(tx, a01 - a00, a00), ra1 = fmaf(tx, a11 - a10, a10);
+  const float rb0 = fmaf(tx, b01 - b00, b00), rb1 = fmaf(tx, b11 - b10, b10);
+  const float dya = ra1 - ra0, dyb = rb1 - rb0;
+  gx = fmaf(go, IS3D ? fmaf(tz, dxb - dxa, dxa) : dxa, gx);
+  gy = fmaf(go, IS3D ? fmaf(tz, dyb - dya, dya) : dya, gy);
+  if (IS3D) gz = fmaf(go, fmaf(ty, rb1 - rb0, rb0) - fmaf(ty, ra1 - ra0, ra0), gz);
+}
+
+template <bool IS3D, bool NOSRC>
+__global__ void __launch_bounds__(TX* TY, NOSRC ? 3 : 2) warp_bwd_fast_kernel(const float* __restrict__ gout, const float* __restrict__ src,
                                                                const float* __restrict__ flow, float* __restrict__ gsrc,
                                                                float* __restrict__ gflow, FastGeom g) {
   const int x = blockIdx.x * TX + threadIdx.x;
@@ -214,7 +233,7 @@ __global__ void __launch_bounds__(TX* TY) warp_bwd_fast_kernel(const float* __re
   const int sW = g.Ws, sHW = g.Hs * g.Ws, sDHW = g.Ds * sHW;
   const float* fb = flow + (size_t)b * g.nd * DHW + y * g.W + x;
   const float* sb = src + (size_t)b * g.C * sDHW;
-  float* gsb = gsrc ? gsrc + (size_t)b * g.C * sDHW : nullptr;
+  float* gsb = (!NOSRC && gsrc) ? gsrc + (size_t)b * g.C * sDHW : nullptr;
   const float* gob = gout + (size_t)b * g.C * DHW + y * g.W + x;
   const int z0c = zc * ZU;
   float f[ZU][3];
@@ -237,46 +256,51 @@ __global__ void __launch_bounds__(TX* TY) warp_bwd_fast_kernel(const float* __re
     const float fx = floorf(cx), fy = floorf(cy), fz = floorf(cz);
     const int x0 = f2i(fx), y0 = f2i(fy), zz0 = f2i(fz);
     const float tx = cx - fx, ty = cy - fy, tz = IS3D ? cz - fz : 0.f;
-    // per-axis validity of the two taps (zeros padding): out-of-volume taps read as 0 and receive no gradient
-    const bool xa = (unsigned)x0 < (unsigned)g.Ws, xb = (unsigned)(x0 + 1) < (unsigned)g.Ws;
-    const bool ya = (unsigned)y0 < (unsigned)g.Hs, yb = (unsigned)(y0 + 1) < (unsigned)g.Hs;
-    const bool za = !IS3D || (unsigned)zz0 < (unsigned)g.Ds, zb = IS3D && (unsigned)(zz0 + 1) < (unsigned)g.Ds;
-    const int xo0 = min(max(x0, 0), g.Ws - 1), xo1 = min(max(x0 + 1, 0), g.Ws - 1);
-    const int yo0 = min(max(y0, 0), g.Hs - 1) * sW, yo1 = min(max(y0 + 1, 0), g.Hs - 1) * sW;
-    const int zo0 = IS3D ? min(max(zz0, 0), g.Ds - 1) * sHW : 0, zo1 = IS3D ? min(max(zz0 + 1, 0), g.Ds - 1) * sHW : 0;
     float gx = 0.f, gy = 0.f, gz = 0.f;
-    for (int c = 0; c < g.C; ++c) {
-      const float go = __ldg(gob + (size_t)c * DHW + z * HW);
-      const float* s = sb + (size_t)c * sDHW;
-      const float a00 = (za && ya && xa) ? __ldg(s + zo0 + yo0 + xo0) : 0.f, a01 = (za && ya && xb) ? __ldg(s + zo0 + yo0 + xo1) : 0.f;
-      const float a10 = (za && yb && xa) ? __ldg(s + zo0 + yo1 + xo0) : 0.f, a11 = (za && yb && xb) ? __ldg(s + zo0 + yo1 + xo1) : 0.f;
-      float b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;
-      if (IS3D) {
-        b00 = (zb && ya && xa) ? __ldg(s + zo1 + yo0 + xo0) : 0.f; b01 = (zb && ya && xb) ? __ldg(s + zo1 + yo0 + xo1) : 0.f;
-        b10 = (zb && yb && xa) ? __ldg(s + zo1 + yo1 + xo0) : 0.f; b11 = (zb && yb && xb) ? __ldg(s + zo1 + yo1 + xo1) : 0.f;
+    const bool interior = (unsigned)x0 < (unsigned)(g.Ws - 1) && (unsigned)y0 < (unsigned)(g.Hs - 1) &&
+                          (!IS3D || (unsigned)zz0 < (unsigned)(g.Ds - 1));
+    if (NOSRC && interior) {
+      const int base = (zz0 * g.Hs + y0) * g.Ws + x0;
+      for (int c = 0; c < g.C; ++c) {
+        const float go = __ldg(gob + (size_t)c * DHW + z * HW);
+        const float* s = sb + (size_t)c * sDHW + base;
+        const float a00 = __ldg(s), a01 = __ldg(s + 1), a10 = __ldg(s + sW), a11 = __ldg(s + sW + 1);
+        float b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;
+        if (IS3D) { b00 = __ldg(s + sHW); b01 = __ldg(s + sHW + 1); b10 = __ldg(s + sHW + sW); b11 = __ldg(s + sHW + sW + 1); }
+        dflow_from_corners<IS3D>(a00, a01, a10, a11, b00, b01, b10, b11, tx, ty, tz, go, gx, gy, gz);
       }
-      if (gflow) {
-        // d/dx: lerp_z(lerp_y(b - a along x));  d/dy, d/dz alike
-        const float dxa = fmaf(ty, (a11 - a10) - (a01 - a00), a01 - a00), dxb = fmaf(ty, (b11 - b10) - (b01 - b00), b01 - b00);
-        const float ra0 = fmaf(tx, a01 - a00, a00), ra1 = fmaf(tx, a11 - a10, a10);
-        const float rb0 = fmaf(tx, b01 - b00, b00), rb1 = fmaf(tx, b11 - b10, b10);
-        const float dya = ra1 - ra0, dyb = rb1 - rb0;
-        gx = fmaf(go, IS3D ? fmaf(tz, dxb - dxa, dxa) : dxa, gx);
-        gy = fmaf(go, IS3D ? fmaf(tz, dyb - dya, dya) : dya, gy);
-        if (IS3D) gz = fmaf(go, fmaf(ty, rb1 - rb0, rb0) - fmaf(ty, ra1 - ra0, ra0), gz);
-      }
-      if (gsb) {
-        float* t = gsb + (size_t)c * sDHW;
-        const float wx0 = 1.f - tx, wy0 = 1.f - ty, wz0 = IS3D ? 1.f - tz : 1.f;
-        if (za && ya && xa) atomicAdd(t + zo0 + yo0 + xo0, go * wx0 * wy0 * wz0);
-        if (za && ya && xb) atomicAdd(t + zo0 + yo0 + xo1, go * tx * wy0 * wz0);
-        if (za && yb && xa) atomicAdd(t + zo0 + yo1 + xo0, go * wx0 * ty * wz0);
-        if (za && yb && xb) atomicAdd(t + zo0 + yo1 + xo1, go * tx * ty * wz0);
+    } else {
+      // per-axis validity of the two taps (zeros padding): out-of-volume taps read as 0 and receive no gradient
+      const bool xa = (unsigned)x0 < (unsigned)g.Ws, xb = (unsigned)(x0 + 1) < (unsigned)g.Ws;
+      const bool ya = (unsigned)y0 < (unsigned)g.Hs, yb = (unsigned)(y0 + 1) < (unsigned)g.Hs;
+      const bool za = !IS3D || (unsigned)zz0 < (unsigned)g.Ds, zb = IS3D && (unsigned)(zz0 + 1) < (unsigned)g.Ds;
+      const int xo0 = min(max(x0, 0), g.Ws - 1), xo1 = min(max(x0 + 1, 0), g.Ws - 1);
+      const int yo0 = min(max(y0, 0), g.Hs - 1) * sW, yo1 = min(max(y0 + 1, 0), g.Hs - 1) * sW;
+      const int zo0 = IS3D ? min(max(zz0, 0), g.Ds - 1) * sHW : 0, zo1 = IS3D ? min(max(zz0 + 1, 0), g.Ds - 1) * sHW : 0;
+      for (int c = 0; c < g.C; ++c) {
+        const float go = __ldg(gob + (size_t)c * DHW + z * HW);
+        const float* s = sb + (size_t)c * sDHW;
+        const float a00 = (za && ya && xa) ? __ldg(s + zo0 + yo0 + xo0) : 0.f, a01 = (za && ya && xb) ? __ldg(s + zo0 + yo0 + xo1) : 0.f;
+        const float a10 = (za && yb && xa) ? __ldg(s + zo0 + yo1 + xo0) : 0.f, a11 = (za && yb && xb) ? __ldg(s + zo0 + yo1 + xo1) : 0.f;
+        float b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;
         if (IS3D) {
-          if (zb && ya && xa) atomicAdd(t + zo1 + yo0 + xo0, go * wx0 * wy0 * tz);
-          if (zb && ya && xb) atomicAdd(t + zo1 + yo0 + xo1, go * tx * wy0 * tz);
-          if (zb && yb && xa) atomicAdd(t + zo1 + yo1 + xo0, go * wx0 * ty * tz);
-          if (zb && yb && xb) atomicAdd(t + zo1 + yo1 + xo1, go * tx * ty * tz);
+          b00 = (zb && ya && xa) ? __ldg(s + zo1 + yo0 + xo0) : 0.f; b01 = (zb && ya && xb) ? __ldg(s + zo1 + yo0 + xo1) : 0.f;
+          b10 = (zb && yb && xa) ? __ldg(s + zo1 + yo1 + xo0) : 0.f; b11 = (zb && yb && xb) ? __ldg(s + zo1 + yo1 + xo1) : 0.f;
+        }
+        if (gflow) dflow_from_corners<IS3D>(a00, a01, a10, a11, b00, b01, b10, b11, tx, ty, tz, go, gx, gy, gz);
+        if (!NOSRC && gsb) {
+          float* t = gsb + (size_t)c * sDHW;
+          const float wx0 = 1.f - tx, wy0 = 1.f - ty, wz0 = IS3D ? 1.f - tz : 1.f;
+          if (za && ya && xa) atomicAdd(t + zo0 + yo0 + xo0, go * wx0 * wy0 * wz0);
+          if (za && ya && xb) atomicAdd(t + zo0 + yo0 + xo1, go * tx * wy0 * wz0);
+          if (za && yb && xa) atomicAdd(t + zo0 + yo1 + xo0, go * wx0 * ty * wz0);
+          if (za && yb && xb) atomicAdd(t + zo0 + yo1 + xo1, go * tx * ty * wz0);
+          if (IS3D) {
+            if (zb && ya && xa) atomicAdd(t + zo1 + yo0 + xo0, go * wx0 * wy0 * tz);
+            if (zb && ya && xb) atomicAdd(t + zo1 + yo0 + xo1, go * tx * wy0 * tz);
+            if (zb && yb && xa) atomicAdd(t + zo1 + yo1 + xo0, go * wx0 * ty * tz);
+            if (zb && yb && xb) atomicAdd(t + zo1 + yo1 + xo1, go * tx * ty * tz);
+          }
         }
       }
     }
@@ -350,8 +374,9 @@ extern "C" int vxm_warp_fwd(const float* src, const float* flow, float* out, int
     FastGeom fg = make_fast_geom(B, C, Ds, Hs, Ws, D, H, W, nd);
     VXM_REQUIRE((size_t)fg.nzc * B <= 65535u, "warp: D*B exceeds the launch grid limit");
     dim3 block(TX, TY, 1), grid((W + TX - 1) / TX, (H + TY - 1) / TY, fg.nzc * B);
-    if (nd == 3) warp_fwd_fast_kernel<true><<<grid, block, 0, st>>>(src, flow, out, fg);
-    else warp_fwd_fast_kernel<false><<<grid, block, 0, st>>>(src, flow, out, fg);
+    if (nd == 3 && C == 1) warp_fwd_fast_kernel<true, true><<<grid, block, 0, st>>>(src, flow, out, fg);
+    else if (nd == 3) warp_fwd_fast_kernel<true, false><<<grid, block, 0, st>>>(src, flow, out, fg);
+    else warp_fwd_fast_kernel<false, false><<<grid, block, 0, st>>>(src, flow, out, fg);
     return check_launch("warp_fwd");
   }
   WarpGeom g = make_geom(B, C, Ds, Hs, Ws, D, H, W, nd);
@@ -372,8 +397,11 @@ extern "C" int vxm_warp_bwd(const float* grad_out, const float* src, const float
     FastGeom fg = make_fast_geom(B, C, Ds, Hs, Ws, D, H, W, nd);
     dim3 block(TX, TY, 1), grid((W + TX - 1) / TX, (H + TY - 1) / TY, fg.nzc * B);
     cudaStream_t st = as_stream(stream);
-    if (nd == 3) warp_bwd_fast_kernel<true><<<grid, block, 0, st>>>(grad_out, src, flow, grad_src, grad_flow, fg);
-    else warp_bwd_fast_kernel<false><<<grid, block, 0, st>>>(grad_out, src, flow, grad_src, grad_flow, fg);
+    const bool nosrc = grad_src == nullptr && grad_flow != nullptr;
+    if (nd == 3 && nosrc) warp_bwd_fast_kernel<true, true><<<grid, block, 0, st>>>(grad_out, src, flow, grad_src, grad_flow, fg);
+    else if (nd == 3) warp_bwd_fast_kernel<true, false><<<grid, block, 0, st>>>(grad_out, src, flow, grad_src, grad_flow, fg);
+    else if (nosrc) warp_bwd_fast_kernel<false, true><<<grid, block, 0, st>>>(grad_out, src, flow, grad_src, grad_flow, fg);
+    else warp_bwd_fast_kernel<false, false><<<grid, block, 0, st>>>(grad_out, src, flow, grad_src, grad_flow, fg);
     return check_launch("warp_bwd");
   }
   WarpGeom g = make_geom(B, C, Ds, Hs, Ws, D, H, W, nd);

@@ -323,6 +323,8 @@ def backward_tape(ctx, g_flow):
     g_flow = _lib.contig(g_flow.float())
     if nd == 2:
         g_flow = g_flow.unsqueeze(2)
+    batch = tc.WgradBatch.get(g_flow.device)
+    batch.reset()
     gz = {}       # conv-output id -> masked gradient (bf16 NDHWC)
     graw = {}     # pool-output id -> raw gradient
     gskip = {}    # encoder-output id -> raw skip gradient
@@ -346,9 +348,9 @@ def backward_tape(ctx, g_flow):
                   and (cv.b is None or (getattr(cv.b, "_vxm_flat_grad", False) and cv.b.grad is not None)))
         if direct:
             tc.conv_wgrad(cv.xa, cv.xb, g_in, cv.cin, cv.cout, kd, up=cv.up, planar_x=cv.planar,
-                          out_w=cv.w.grad, out_b=None if cv.b is None else cv.b.grad)
+                          out_w=cv.w.grad, out_b=None if cv.b is None else cv.b.grad, batch=batch)
         else:
-            gw, gb = tc.conv_wgrad(cv.xa, cv.xb, g_in, cv.cin, cv.cout, kd, up=cv.up, planar_x=cv.planar)
+            gw, gb = tc.conv_wgrad(cv.xa, cv.xb, g_in, cv.cin, cv.cout, kd, up=cv.up, planar_x=cv.planar, batch=batch)
             grads[cv.w] = gw.squeeze(2) if nd == 2 else gw
             if cv.b is not None:
                 grads[cv.b] = gb
@@ -385,6 +387,7 @@ def backward_tape(ctx, g_flow):
             gz[cv.a_id] = _sumpool_mask(g_up, tensors[cv.a_id], nd, _slope_of(ctx, cv.a_id))   # grad wrt upsample(a): sum children
             del g_up
             gskip[cv.b_id] = g_sk
+    batch.flush()     # one launch reduces every layer's per-CTA partials (fixed order: deterministic)
     return grads
 
 

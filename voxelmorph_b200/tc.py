@@ -97,9 +97,18 @@ def _planar_args(planar):
 _wgrad_ws = {}
 
 
-def conv_wgrad(xa, xb, gz, cin, cout, kd, up=False, planar_x=None, planar_g=None, need_bias=True, out_w=None, out_b=None):
-    """fp32 grad_w (cout, cin, kd, 3, 3) and grad_b (cout) from the layer input (xa/xb or planar_x) and gz."""
+def conv_wgrad(xa, xb, gz, cin, cout, kd, up=False, planar_x=None, planar_g=None, need_bias=True, out_w=None, out_b=None, batch=None):
+    """fp32 grad_w (cout, cin, kd, 3, 3) and grad_b (cout) from the layer input (xa/xb or planar_x) and gz.
+    `batch` (a WgradBatch): only the tcgen05 partial-sum kernels are launched now, the reduction into gw / gb happens at
+    `batch.flush()` together with every other layer's."""
     lib = _lib.load()
+    if batch is not None and wgrad_deferrable(xa, xb, gz, planar_x, planar_g):
+        dev = gz.device
+        accumulate = out_w is not None
+        gw = out_w if accumulate else torch.empty((cout, cin, kd, 3, 3), dtype=torch.float32, device=dev)
+        gb = out_b if accumulate else (torch.empty(cout, dtype=torch.float32, device=dev) if need_bias else None)
+        batch.add(xa, xb, gz, gw, gb, cin, cout, kd, up, accumulate)
+        return gw, gb
     ref = gz if gz is not None else planar_g[0]
     dev = ref.device
     if gz is not None:
@@ -297,3 +306,72 @@ def pool_split(x, nd):
     _lib.check(lib.vxm_pool2_split_ndhwc_bf16(_lib.ptr(xh), _lib.ptr(xl), _lib.ptr(yh), _lib.ptr(yl), B, Dc, H // 2, W // 2, C, nd,
                                               _lib.stream_ptr()), "vxm_pool2_split_ndhwc_bf16")
     return yh, yl
+
+
+# ---- deferred weight-gradient reduction: every layer's partials reduced by ONE launch at the end of the backward pass ----
+
+class WgradBatch:
+    """Collects the pending reductions of the tcgen05 weight-gradient kernels of one backward pass
+    (vxm_conv3d_tc_wgrad2_partial) and reduces them all in one launch (`flush`).  One instance per (device, stream);
+    the workspace is persistent (512 MB: the default 3-D U-Net at 160x192x224 needs ~200 MB of per-CTA partials)."""
+
+    _cache = {}
+    WORK_BYTES = 512 << 20
+
+    @classmethod
+    def get(cls, device):
+        key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+        b = cls._cache.get(key)
+        if b is None:
+            b = cls._cache[key] = cls(device)
+        return b
+
+    def __init__(self, device):
+        lib = _lib.load()
+        self.dev = device
+        self.dsz = int(lib.vxm_conv3d_tc_wgrad2_desc_bytes())
+        self.maxn = int(lib.vxm_conv3d_tc_wgrad2_max_pending())
+        self.host = ctypes.create_string_buffer(self.dsz * self.maxn)
+        self.n = ctypes.c_int(0)
+        self.used = ctypes.c_size_t(0)
+        self.off = 0
+        self.work = torch.empty(self.WORK_BYTES, dtype=torch.uint8, device=device)
+
+    def add(self, xa, xb, gz, gw, gb, cin, cout, kd, up, accumulate):
+        lib = _lib.load()
+        need = int(lib.vxm_conv3d_tc_wgrad2_partial_bytes(kd))
+        if self.off + need > self.WORK_BYTES or self.n.value + 2 > self.maxn:
+            self.flush()
+        B, D, H, W, Cg = gz.shape
+        Ca = 0 if xa is None else xa.shape[-1]
+        Cb = 0 if xb is None else xb.shape[-1]
+        _lib.check(lib.vxm_conv3d_tc_wgrad2_partial(_lib.ptr(xa), _lib.ptr(xb), _lib.ptr(gz), _lib.ptr(gw), _lib.ptr(gb),
+                                                    ctypes.c_void_p(self.work.data_ptr() + self.off), self.WORK_BYTES - self.off,
+                                                    ctypes.byref(self.used), ctypes.cast(self.host, ctypes.c_void_p), ctypes.byref(self.n),
+                                                    B, D, H, W, Ca, Cb, 1 if up else 0, cin, Cg, cout, kd, 1 if accumulate else 0,
+                                                    _lib.stream_ptr()), "vxm_conv3d_tc_wgrad2_partial")
+        self.off += int(self.used.value)
+
+    def reset(self):
+        """Drop pending reductions (after an error mid-backward)."""
+        self.n.value = 0
+        self.off = 0
+
+    def flush(self):
+        if self.n.value:
+            _lib.check(_lib.load().vxm_conv3d_tc_wgrad2_flush(ctypes.cast(self.host, ctypes.c_void_p), self.n.value, _lib.stream_ptr()),
+                       "vxm_conv3d_tc_wgrad2_flush")
+        self.n.value = 0
+        self.off = 0
+
+
+def wgrad_deferrable(xa, xb, gz, planar_x=None, planar_g=None):
+    import os
+    if os.environ.get("VXM_B200_WGRAD_DEFER", "1") != "1" or os.environ.get("VXM_B200_WGRAD", "")[:1] == "o":
+        return False
+    if gz is None or planar_x is not None or planar_g is not None:
+        return False
+    ok = lambda c: c in (8, 16, 32)  # noqa: E731
+    ca = 0 if xa is None else xa.shape[-1]
+    cb = 0 if xb is None else xb.shape[-1]
+    return (ca == 0 or ok(ca)) and (cb == 0 or ok(cb)) and ca + cb > 0 and ok(gz.shape[-1])
