@@ -34,6 +34,12 @@ struct ConvSArgs {
   int tiles_h, tiles_w, dchunk, nchunks, nitems, nslot;
   uint32_t wbytes;
   const float* acc_in; void* out_lo;
+  // TMA tile staging of the A operand: bit g of tma_mask = channel group g of every slab arrives as ONE tiled tensor copy
+  // (cp.async.bulk.tensor.5d, box {G channels, 32 columns, HT + 2 rows}) of tensor map tm[g], starting at channel tc0[g];
+  // zero padding is the copy's out-of-bounds fill.  Groups read through the nearest-neighbour upsampler (decoder concat
+  // layers), the 64-channel group that interleaves two sources and the 8-plane image input stay on the cp.async loader.
+  int tma_mask, tc0[2];
+  alignas(64) CUtensorMap tm[2];
 };
 
 // byte offset inside a swizzled K-major tile whose rows are `width` bytes (32, 64 or 128): Swizzle<log2(width/16),4,3>
@@ -55,7 +61,7 @@ __device__ __forceinline__ uint64_t make_desc_kmajor_swz(uint32_t saddr, uint32_
 // ACC: the split-precision epilogue (acc_in / out_mode 2, 3) is compiled in; the plain kernels (ACC = false) keep the
 // round-1 epilogue — with the extra live registers the 32-channel variants spilled and lost up to 1.8x.
 template <int KD, int G0, int G1, int COUT, int HT, bool ACC>
-__global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const ConvSArgs a) {
+__global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const __grid_constant__ ConvSArgs a) {
   constexpr int SROWS = (HT + 2) * WT;
   constexpr int NH = HT / 4;
   constexpr int W0 = G0 * 2, W1 = G1 * 2;                 // row bytes of the two channel groups
@@ -82,8 +88,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const ConvSArgs a
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t tmem_cols = NACC * NN <= 128 ? 128u : (NACC * NN <= 256 ? 256u : 512u);
 
+  const bool tma0 = a.tma_mask & 1, tma1 = (a.tma_mask & 2) != 0;
+  const bool all_tma = tma0 && (G1 == 0 || tma1);        // no cp.async traffic at all: one producer thread
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NSLOT; ++i) { mbar_init(&full[i], NLOADER); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < NSLOT; ++i) { mbar_init(&full[i], all_tma ? 1 : NLOADER); mbar_init(&empty[i], 1); }
     for (int i = 0; i < NACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
     mbar_init(wbar, 1);
     fence_barrier_init();
@@ -111,7 +119,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const ConvSArgs a
     const int nca8 = a.Ca >> 3;
     constexpr int nchunk = NC8 * SROWS;
     constexpr int KMAX = (nchunk + NLOADER - 1) / NLOADER;
-    for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+    if (lt == 0) {
+      if (tma0) tma_prefetch_desc(&a.tm[0]);
+      if (tma1) tma_prefetch_desc(&a.tm[1]);
+    }
+    const uint32_t tma_bytes = (tma0 ? SLAB0 : 0u) + (tma1 ? SLAB1 : 0u);
+    for (int item = blockIdx.x; item < a.nitems && !(all_tma && lt != 0); item += gridDim.x) {
       const int wt = item % a.tiles_w, ht = (item / a.tiles_w) % a.tiles_h;
       const int ch = (item / HW_tiles) % a.nchunks, b = item / (HW_tiles * a.nchunks);
       const int h0 = ht * HT, w0 = wt * WUSE, d0 = ch * a.dchunk, d1 = min(d0 + a.dchunk, a.D);
@@ -129,7 +142,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const ConvSArgs a
           const int h = h0 - 1 + r, w = w0 - 1 + c;
           doff[k] = c8 < G0 / 8 ? swz((uint32_t)row * W0 + (uint32_t)c8 * 16u, W0)
                                 : SLAB0 + swz((uint32_t)row * W1 + (uint32_t)(c8 - G0 / 8) * 16u, W1 ? W1 : 32);
-          if (h >= 0 && h < a.H && w >= 0 && w < a.W && !(halfk && c8 > 0)) {
+          if (c8 < G0 / 8 ? tma0 : tma1) soff[k] = -2;      // this chunk's group arrives by tensor copy
+          else if (h >= 0 && h < a.H && w >= 0 && w < a.W && !(halfk && c8 > 0)) {
             if (c8 < nca8) soff[k] = (((a.up ? h >> 1 : h) * Wa + (a.up ? w >> 1 : w)) * a.Ca + c8 * 8) << 1;
             else soff[k] = (((h * a.W + w) * a.Cb + (c8 - nca8) * 8) << 1) | 1;
           }
@@ -142,15 +156,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const ConvSArgs a
         const __nv_bfloat16* baseA = a.xa ? a.xa + (((size_t)b * Da + (dok ? (a.upd ? ds >> 1 : ds) : 0)) * Ha * Wa) * a.Ca : nullptr;
         const __nv_bfloat16* baseB = a.xb ? a.xb + (((size_t)b * a.D + (dok ? ds : 0)) * a.H * a.W) * a.Cb : nullptr;
         const __nv_bfloat16* dummy = a.xa ? a.xa : a.xb;
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-          if (lt + k * NLOADER < nchunk) {
-            const bool ok = dok && soff[k] >= 0;
-            const __nv_bfloat16* src = ok ? ((soff[k] & 1) ? baseB : baseA) + (soff[k] >> 1) : dummy;
-            cp_async16(slab + doff[k], src, ok ? 16u : 0u);
-          }
+        if (lt == 0 && tma_bytes) {
+          if (all_tma) mbar_expect_tx(&full[slot], tma_bytes);
+          else mbar_expect_tx_noarrive(&full[slot], tma_bytes);
+          if (tma0) tma_load_5d(slab, &a.tm[0], a.tc0[0], w0 - 1, h0 - 1, ds, b, &full[slot]);
+          if (tma1) tma_load_5d(slab + SLAB0, &a.tm[1], a.tc0[1], w0 - 1, h0 - 1, ds, b, &full[slot]);
         }
-        cp_async_arrive_noinc(&full[slot]);
+        if (!all_tma) {
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k) {
+            if (lt + k * NLOADER < nchunk && soff[k] != -2) {
+              const bool ok = dok && soff[k] >= 0;
+              const __nv_bfloat16* src = ok ? ((soff[k] & 1) ? baseB : baseA) + (soff[k] >> 1) : dummy;
+              cp_async16(slab + doff[k], src, ok ? 16u : 0u);
+            }
+          }
+          cp_async_arrive_noinc(&full[slot]);
+        }
         if (++slot == (uint32_t)NSLOT) { slot = 0; lphase ^= 1; }
       }
     }
@@ -453,6 +475,28 @@ static void groups_of(int cin, int* g0, int* g1) {
   else { *g0 = 64; *g1 = 0; }
 }
 
+// Which channel groups of the slab can be staged by tiled tensor copies: a group whose channels all come from one source
+// tensor that is read at its own resolution.  VXM_B200_TMA=0 keeps every group on the cp.async loader (A/B switch).
+static int plan_tma(ConvSArgs& a, int g0, int g1, int HTv) {
+  a.tma_mask = 0;
+  a.tc0[0] = a.tc0[1] = 0;
+  const char* e = getenv("VXM_B200_TMA");
+  if (e && e[0] == '0') return 0;
+  const int lo[2] = {0, g0}, hi[2] = {g0, g0 + g1};
+  for (int g = 0; g < 2; ++g) {
+    if (hi[g] == lo[g]) continue;
+    const void* base = nullptr;
+    int C = 0, c0 = 0;
+    if (a.xa && hi[g] <= a.Ca && !a.up) { base = a.xa; C = a.Ca; c0 = lo[g]; }
+    else if (a.xb && lo[g] >= a.Ca && hi[g] <= a.Ca + a.Cb) { base = a.xb; C = a.Cb; c0 = lo[g] - a.Ca; }
+    if (!base) continue;
+    if (tc::make_act_tmap(&a.tm[g], base, a.B, a.D, a.H, a.W, C, hi[g] - lo[g], WT, HTv + 2) != 0) return -1;
+    a.tma_mask |= 1 << g;
+    a.tc0[g] = c0;
+  }
+  return 0;
+}
+
 }  // namespace tcs
 }  // namespace vxm
 
@@ -583,6 +627,7 @@ static int conv_tcs_launch(const void* xa, const void* xb, const void* wpk, cons
   size_t smem = fixed + (size_t)nslot * slab;
   int grid = a.nitems < nsm ? a.nitems : nsm;
   cudaStream_t st = as_stream(stream);
+  if (plan_tma(a, g0, g1, HTv) != 0) return VXM_ERR_CUDA;
   const bool acc_epi = acc_in != nullptr || out_mode >= 2;
 #define VXM_TCS_LAUNCH(KD_, G0_, G1_, CO_, HT_)                                                                                   \
   do {                                                                                                                            \

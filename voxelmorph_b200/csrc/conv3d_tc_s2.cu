@@ -21,6 +21,8 @@
 //                   accumulator), which waits for it before issuing e+3; every barrier has one waiter, consecutive phases.
 // To try it: copy this file into voxelmorph_b200/csrc/, declare vxm_conv3d_tcs2_fwd in include/vxm_b200.h + _lib.py (same
 // signature as vxm_conv3d_tcs_fwd; weights packed by vxm_conv3d_tcs_pack) and route tc.conv_fwd_t to it.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace vxm {
@@ -41,6 +43,13 @@ struct ConvSArgs {
   float slope;
   int tiles_h, tiles_w, dchunk, nchunks, nitems, nslot;
   uint32_t wbytes;
+  // TMA tile staging of the A operand (see conv3d_tc_s.cu): bit g of tma_mask = channel group g of every slab arrives as one
+  // cp.async.bulk.tensor.5d of tensor map tm[g] starting at channel tc0[g]; zero padding = the copy's out-of-bounds fill
+  int tma_mask, tc0[2];
+  // ablation switches for profiling only (VXM_B200_TCS_DBG, never set in production): 1 = no MMAs issued, 2 = no TMEM
+  // read-out, 4 = no global stores / mask loads, 8 = no slab copies
+  int dbg;
+  alignas(64) CUtensorMap tm[2];
 };
 
 // byte offset inside a swizzled K-major tile whose rows are `width` bytes (32, 64 or 128): Swizzle<log2(width/16),4,3>
@@ -60,7 +69,7 @@ __device__ __forceinline__ uint64_t make_desc_kmajor_swz(uint32_t saddr, uint32_
 // HT = 8: one slab step feeds TWO 4-row accumulators (one per epilogue group), halving the per-step issue / barrier
 // overhead that bounds the thin layers and cutting the halo re-reads from 1.5x to 1.25x.
 template <int KD, int G0, int G1, int COUT, int HT>
-__global__ void __launch_bounds__(NTHREADS, 1) conv_tcs2_kernel(const ConvSArgs a) {
+__global__ void __launch_bounds__(NTHREADS, 1) conv_tcs2_kernel(const __grid_constant__ ConvSArgs a) {
   static_assert(HT == 8, "alternating issuers are written for 8-row tiles");
   constexpr int SROWS = (HT + 2) * WT;
   constexpr int NH = HT / 4;
@@ -88,8 +97,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs2_kernel(const ConvSArgs 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t tmem_cols = NACC * NN <= 128 ? 128u : (NACC * NN <= 256 ? 256u : 512u);
 
+  const bool tma0 = a.tma_mask & 1, tma1 = (a.tma_mask & 2) != 0;
+  const bool all_tma = tma0 && (G1 == 0 || tma1);        // no cp.async traffic at all: one producer thread
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NSLOT; ++i) { mbar_init(&full[i], NLOADER); mbar_init(&empty[i], 2); }   // one arrival per issuer
+    for (int i = 0; i < NSLOT; ++i) { mbar_init(&full[i], all_tma ? 1 : NLOADER); mbar_init(&empty[i], 2); }   // one arrival per issuer
     for (int i = 0; i < NACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); mbar_init(&tempty[MAXACC + i], 128); }
     mbar_init(wbar, 1);
     fence_barrier_init();
@@ -117,7 +128,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs2_kernel(const ConvSArgs 
     const int nca8 = a.Ca >> 3;
     constexpr int nchunk = NC8 * SROWS;
     constexpr int KMAX = (nchunk + NLOADER - 1) / NLOADER;
-    for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+    if (lt == 0) {
+      if (tma0) tma_prefetch_desc(&a.tm[0]);
+      if (tma1) tma_prefetch_desc(&a.tm[1]);
+    }
+    const uint32_t tma_bytes = (tma0 ? SLAB0 : 0u) + (tma1 ? SLAB1 : 0u);
+    const bool nocopy = a.dbg & 8;
+    for (int item = blockIdx.x; item < a.nitems && !(all_tma && lt != 0); item += gridDim.x) {
       const int wt = item % a.tiles_w, ht = (item / a.tiles_w) % a.tiles_h;
       const int ch = (item / HW_tiles) % a.nchunks, b = item / (HW_tiles * a.nchunks);
       const int h0 = ht * HT, w0 = wt * WUSE, d0 = ch * a.dchunk, d1 = min(d0 + a.dchunk, a.D);
@@ -135,7 +152,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs2_kernel(const ConvSArgs 
           const int h = h0 - 1 + r, w = w0 - 1 + c;
           doff[k] = c8 < G0 / 8 ? swz((uint32_t)row * W0 + (uint32_t)c8 * 16u, W0)
                                 : SLAB0 + swz((uint32_t)row * W1 + (uint32_t)(c8 - G0 / 8) * 16u, W1 ? W1 : 32);
-          if (h >= 0 && h < a.H && w >= 0 && w < a.W && !(halfk && c8 > 0)) {
+          if (c8 < G0 / 8 ? tma0 : tma1) soff[k] = -2;      // this chunk's group arrives by tensor copy
+          else if (h >= 0 && h < a.H && w >= 0 && w < a.W && !(halfk && c8 > 0)) {
             if (c8 < nca8) soff[k] = (((a.up ? h >> 1 : h) * Wa + (a.up ? w >> 1 : w)) * a.Ca + c8 * 8) << 1;
             else soff[k] = (((h * a.W + w) * a.Cb + (c8 - nca8) * 8) << 1) | 1;
           }
@@ -148,15 +166,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs2_kernel(const ConvSArgs 
         const __nv_bfloat16* baseA = a.xa ? a.xa + (((size_t)b * Da + (dok ? (a.upd ? ds >> 1 : ds) : 0)) * Ha * Wa) * a.Ca : nullptr;
         const __nv_bfloat16* baseB = a.xb ? a.xb + (((size_t)b * a.D + (dok ? ds : 0)) * a.H * a.W) * a.Cb : nullptr;
         const __nv_bfloat16* dummy = a.xa ? a.xa : a.xb;
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-          if (lt + k * NLOADER < nchunk) {
-            const bool ok = dok && soff[k] >= 0;
-            const __nv_bfloat16* src = ok ? ((soff[k] & 1) ? baseB : baseA) + (soff[k] >> 1) : dummy;
-            cp_async16(slab + doff[k], src, ok ? 16u : 0u);
+        if (lt == 0 && tma_bytes) {
+          if (nocopy) { if (all_tma) mbar_arrive(&full[slot]); }
+          else {
+            if (all_tma) mbar_expect_tx(&full[slot], tma_bytes);
+            else mbar_expect_tx_noarrive(&full[slot], tma_bytes);
+            if (tma0) tma_load_5d(slab, &a.tm[0], a.tc0[0], w0 - 1, h0 - 1, ds, b, &full[slot]);
+            if (tma1) tma_load_5d(slab + SLAB0, &a.tm[1], a.tc0[1], w0 - 1, h0 - 1, ds, b, &full[slot]);
           }
         }
-        cp_async_arrive_noinc(&full[slot]);
+        if (!all_tma) {
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k) {
+            if (lt + k * NLOADER < nchunk && soff[k] != -2 && !nocopy) {
+              const bool ok = dok && soff[k] >= 0;
+              const __nv_bfloat16* src = ok ? ((soff[k] & 1) ? baseB : baseA) + (soff[k] >> 1) : dummy;
+              cp_async16(slab + doff[k], src, ok ? 16u : 0u);
+            }
+          }
+          cp_async_arrive_noinc(&full[slot]);
+        }
         if (++slot == (uint32_t)NSLOT) { slot = 0; lphase ^= 1; }
       }
     }
@@ -217,6 +246,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs2_kernel(const ConvSArgs 
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + acc * (uint32_t)NN;
             if (elect_one()) {
+              if (!(a.dbg & 1)) {
 #pragma unroll
               for (int kd = 0; kd < KD; ++kd) {
 #pragma unroll
@@ -235,6 +265,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs2_kernel(const ConvSArgs 
                     umma_f16(tmem_d, adesc, bdesc, idesc, 1u);
                   }
                 }
+              }
               }
               umma_commit(&tfull[acc]);
               if (hb == NH - 1) {
@@ -303,7 +334,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs2_kernel(const ConvSArgs 
         const size_t vox = (((size_t)b * a.D + d) * a.H + h) * a.W + w;
         // prefetch the LeakyReLU-derivative mask of this voxel before waiting for the tensor core
         uint4 mreg[COUT / 8];
-        if (a.mask && valid) {
+        if (a.mask && valid && !(a.dbg & 4)) {
 #pragma unroll
           for (int q = 0; q < COUT / 8; ++q)
             if (q * 8 < a.Cout) mreg[q] = __ldg(reinterpret_cast<const uint4*>(a.mask + vox * a.Cout) + q);
@@ -317,10 +348,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs2_kernel(const ConvSArgs 
 #pragma unroll
         for (int c0 = 0; c0 < COUT; c0 += 16) {
           uint32_t r0[16], r1[16], r2[16];
-          tmem_ld16(taddr + c0, r0);
-          tmem_ld16(taddr + COUT + c0, r1);
-          tmem_ld16(taddr + 2 * COUT + c0, r2);
-          tmem_ld_wait();
+          if (a.dbg & 2) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) r0[c] = r1[c] = r2[c] = 0u;
+          } else {
+            tmem_ld16(taddr + c0, r0);
+            tmem_ld16(taddr + COUT + c0, r1);
+            tmem_ld16(taddr + 2 * COUT + c0, r2);
+            tmem_ld_wait();
+          }
           if (c0 + 16 >= COUT) {          // last TMEM read of this accumulator
             tc_fence_before();
             mbar_arrive(&tempty[((((ev - 1u) + (uint32_t)NACC) >> 1) & 1u) * MAXACC + acc]);   // issuer of event e + NACC, e = ev - 1
@@ -332,7 +368,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs2_kernel(const ConvSArgs 
             const float p2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[c]), 1);
             v[c] = (p0 + __uint_as_float(r1[c])) + p2;      // out[w'] = P0[w'-1] + P1[w'] + P2[w'+1]
           }
-          if (valid && c0 < a.Cout) {
+          if (valid && c0 < a.Cout && !(a.dbg & 4)) {
             if (a.out_mode == 0) {
 #pragma unroll
               for (int q = 0; q < 16; q += 8) {
@@ -426,6 +462,27 @@ extern "C" int vxm_conv3d_tcs2_fwd(const void* xa, const void* xb, const void* w
   const size_t smem = fixed + (size_t)nslot * slab;
   const int grid = a.nitems < nsm ? a.nitems : nsm;
   cudaStream_t st = as_stream(stream);
+  {
+    const char* e = getenv("VXM_B200_TCS_DBG");
+    a.dbg = e ? atoi(e) : 0;
+    // TMA plan: a channel group whose channels all come from one source tensor read at its own resolution (VXM_B200_TMA=0: none)
+    a.tma_mask = 0; a.tc0[0] = a.tc0[1] = 0;
+    const char* t = getenv("VXM_B200_TMA");
+    if (!(t && t[0] == '0')) {
+      const int lo[2] = {0, g0}, hi[2] = {g0, g0 + g1};
+      for (int g = 0; g < 2; ++g) {
+        if (hi[g] == lo[g]) continue;
+        const void* base = nullptr;
+        int C = 0, c0 = 0;
+        if (a.xa && hi[g] <= Ca && !up) { base = xa; C = Ca; c0 = lo[g]; }
+        else if (a.xb && lo[g] >= Ca && hi[g] <= Ca + Cb) { base = xb; C = Cb; c0 = lo[g] - Ca; }
+        if (!base) continue;
+        if (tc::make_act_tmap(&a.tm[g], base, B, D, H, W, C, hi[g] - lo[g], WT, 10) != 0) return VXM_ERR_CUDA;
+        a.tma_mask |= 1 << g;
+        a.tc0[g] = c0;
+      }
+    }
+  }
 #define VXM_TCS2_LAUNCH(KD_, G0_, G1_, CO_)                                                                                    \
   do {                                                                                                                        \
     VXM_CUDA(cudaFuncSetAttribute(conv_tcs2_kernel<KD_, G0_, G1_, CO_, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \

@@ -1,6 +1,7 @@
 // Thin PTX wrappers for the sm_100a tensor-core path: mbarrier, cp.async, bulk (TMA) copies,
 // tcgen05 alloc / mma / commit / ld, and UMMA descriptor encoders.
 #pragma once
+#include <cuda.h>        // CUtensorMap (types only: the encoder is resolved at run time, libcuda is not linked)
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -75,6 +76,29 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+
+// ---------------------------------------------------------------- tiled tensor copy (TMA, 5-D) ------
+// A bf16 channels-last activation (B, D, H, W, C) is described to the TMA unit as the 5-D tensor {C, W, H, D, B}; one
+// copy moves a box {G channels, 32 columns, rows, 1 slice, 1 batch item} into shared memory with the 32 / 64 / 128-byte
+// swizzle the UMMA K-major operand layouts use (row = voxel, channels contiguous).  Coordinates may lie outside the
+// tensor (negative, or >= the extent): those elements arrive as zeros, which is exactly the convolution's zero padding.
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst_smem, const void* tmap, int c0, int c1, int c2, int c3, int c4, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
+      : "memory");
+}
+// raises the barrier's pending transaction count without arriving (the caller arrives separately)
+__device__ __forceinline__ void mbar_expect_tx_noarrive(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+// Host side: encode the tensor map of a bf16 (B, D, H, W, C) activation with box {boxC, boxW, boxH, 1, 1}.  boxC * 2 bytes
+// is the shared-memory row width (32 / 64 / 128) and selects the swizzle mode.  Returns 0, or -1 with vxm_last_error set.
+int make_act_tmap(CUtensorMap* out, const void* base, int B, int D, int H, int W, int C, int boxC, int boxW, int boxH);
 
 // ---------------------------------------------------------------- TMEM ----------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {  // whole warp
