@@ -30,15 +30,19 @@ def layer(name, shape, Ca, Cout, mask=False):
     ws_, cps = tc.pack_weights_t(w, variant="s")
     m = torch.randn((1,) + shape + (Cout,), device=dev).to(torch.bfloat16) if mask else None
     res = {}
-    for tma in ("1", "0"):
-        os.environ["VXM_B200_TMA"] = tma
-        for dbg, label in ((0, "full"), (8, "no_copy"), (1, "no_mma"), (2, "no_tmem_ld"), (4, "no_store"), (7, "loader_only"),
+    bias = None if mask else b
+    for cfg in (os.environ.get("ABLATE_CFGS", "tma1_nacc6_epi1,tma1_nacc3_epi1,tma1_nacc6_epi0,tma0_nacc3_epi0")).split(","):
+        kv = dict((x[:-1], x[-1]) for x in cfg.split("_"))
+        os.environ["VXM_B200_TMA"] = kv.get("tma", "1")
+        os.environ["VXM_B200_TCS_NACC"] = kv.get("nacc", "6")
+        os.environ["VXM_B200_TCS_EPI"] = kv.get("epi", "1")
+        for dbg, label in ((0, "full"), (1, "no_mma"), (4, "no_store"), (7, "loader_only"),
                            (14, "mma_only"), (13, "tmem_ld_only"), (11, "store_only"), (15, "skeleton")):
             os.environ["VXM_B200_TCS_DBG"] = str(dbg)
-            t = timeit(lambda: tc.conv_fwd_t(xa, None, ws_, cps, b, Cout, 3, slope=0.2, mask=m))
-            res["tma%s_%s" % (tma, label)] = round(t * 1e3, 1)
-    os.environ["VXM_B200_TCS_DBG"] = "0"
-    os.environ["VXM_B200_TMA"] = "1"
+            t = timeit(lambda: tc.conv_fwd_t(xa, None, ws_, cps, bias, Cout, 3, slope=0.2, mask=m))
+            res["%s:%s" % (cfg, label)] = round(t * 1e3, 1)
+    for k in ("VXM_B200_TCS_DBG", "VXM_B200_TMA", "VXM_B200_TCS_NACC", "VXM_B200_TCS_EPI"):
+        os.environ.pop(k, None)
     print(json.dumps(dict(layer=name, us=res)), flush=True)
 
 

@@ -31,7 +31,7 @@ namespace tcs2 {
 using namespace vxm::tc;
 
 constexpr int WT = 32, WUSE = 30;      // tile: HT (4 or 8) rows x 32 columns (30 written), slab = (HT + 2) x 32 voxel rows
-constexpr int MAXSLOT = 8, MAXACC = 4;
+constexpr int MAXSLOT = 8, MAXACC = 6;
 constexpr int NLOADER = 64, NTHREADS = 512;   // warps 0-3 epilogue group 0, 4 / 5 MMA issuers (even / odd steps), 6-7 loader, 8-11 / 12-15 epilogue groups 1 / 2
 
 struct ConvSArgs {
@@ -49,6 +49,11 @@ struct ConvSArgs {
   // ablation switches for profiling only (VXM_B200_TCS_DBG, never set in production): 1 = no MMAs issued, 2 = no TMEM
   // read-out, 4 = no global stores / mask loads, 8 = no slab copies
   int dbg;
+  int nacc;       // TMEM accumulators in flight: 3 or 6
+  // profiling aid (VXM_B200_TCS_TRACE = device address of a uint64 buffer, never set in production): CTA 0 records
+  // clock64() stamps, trace[role * 4096 + n * 8 + k] for its n-th step / slab / tile (n < 512) at point k of role
+  // 0 / 1 = MMA issuers, 2 = slab producer, 3 / 4 / 5 = epilogue groups (their first warp)
+  unsigned long long* trace;
   alignas(64) CUtensorMap tm[2];
 };
 
@@ -68,7 +73,13 @@ __device__ __forceinline__ uint64_t make_desc_kmajor_swz(uint32_t saddr, uint32_
 
 // HT = 8: one slab step feeds TWO 4-row accumulators (one per epilogue group), halving the per-step issue / barrier
 // overhead that bounds the thin layers and cutting the halo re-reads from 1.5x to 1.25x.
-template <int KD, int G0, int G1, int COUT, int HT>
+// EPI: epilogue specialisation.  The generic epilogue (0) decides bias / activation / mask / output layout / channel split
+// per tile at run time and costs ~430 issued instructions per warp and tile: at one instruction per clock and scheduler the
+// three epilogue warps of a scheduler then bound the thin layers (ablation: the barrier skeleton alone ran 92 us of the
+// 180 us of the 16->16 layer, profiles/r2_conv_ablation.md).  1 = forward (bias + LeakyReLU, 0 <= slope <= 1, bf16
+// channels-last, all COUT channels real), 2 = dgrad (LeakyReLU derivative from the saved activation, no bias): straight-line
+// code with the pointers advanced incrementally.
+template <int KD, int G0, int G1, int COUT, int HT, int EPI>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs2_kernel(const __grid_constant__ ConvSArgs a) {
   static_assert(HT == 8, "alternating issuers are written for 8-row tiles");
   constexpr int SROWS = (HT + 2) * WT;
@@ -79,7 +90,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs2_kernel(const __grid_con
   constexpr int NN = 3 * COUT;   // MMA N: (kw, co)
   // TMEM accumulators in flight = epilogue groups in use: group g owns accumulator g, so every mbarrier is waited on
   // phase by phase (a group that skipped ahead on a barrier would alias its parity)
-  constexpr int NACC = (3 * NN <= 512) ? 3 : 2;
+  // Accumulators in flight: 3 (group g owns accumulator g) or 6 (group g owns g and g + 3, alternately).  The round trip
+  // commit -> epilogue wake-up -> TMEM read -> release -> issuer wake-up measured ~1300 clk even with the MMAs and the
+  // read-out switched off (profiles/r2_conv_ablation.md): with 3 accumulators that latency, not the tensor pipe, paces the
+  // 16-channel layers.  A group still never skips a phase of a barrier it waits on (it owns its accumulators).
+  const int NACC = a.nacc;
   extern __shared__ __align__(1024) uint8_t smem[];
   const bool halfk = (a.Ca + a.Cb == 8);                  // 8 real channels in a 16-channel group: chunk 1 is zero-filled
   constexpr uint32_t slab_bytes = SLAB0 + SLAB1;
@@ -95,13 +110,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs2_kernel(const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr uint32_t tmem_cols = NACC * NN <= 128 ? 128u : (NACC * NN <= 256 ? 256u : 512u);
+  const uint32_t tmem_cols = NACC * NN <= 128 ? 128u : (NACC * NN <= 256 ? 256u : 512u);
 
   const bool tma0 = a.tma_mask & 1, tma1 = (a.tma_mask & 2) != 0;
   const bool all_tma = tma0 && (G1 == 0 || tma1);        // no cp.async traffic at all: one producer thread
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSLOT; ++i) { mbar_init(&full[i], all_tma ? 1 : NLOADER); mbar_init(&empty[i], 2); }   // one arrival per issuer
-    for (int i = 0; i < NACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); mbar_init(&tempty[MAXACC + i], 128); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); mbar_init(&tempty[MAXACC + i], 4); }   // one arrival per epilogue warp
     mbar_init(wbar, 1);
     fence_barrier_init();
   }
@@ -119,11 +134,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs2_kernel(const __grid_con
     }
   }
   const int HW_tiles = a.tiles_h * a.tiles_w;
+  unsigned long long* const trace = blockIdx.x == 0 ? a.trace : nullptr;
+#define VXM_TR(role_, n_, k_)                                                                             \
+  do {                                                                                                    \
+    if (trace && (n_) < 512u && lane == 0) trace[(role_) * 4096 + (n_) * 8 + (k_)] = clock64();           \
+  } while (0)
 
   if (warp == 6 || warp == 7) {
     // ================================ LOADER (64 threads) ================================
     const int lt = threadIdx.x - 6 * 32;
     uint32_t slot = 0, lphase = 1;   // producer side: the first lap passes on the fresh barriers
+    uint32_t ltr = 0;
     const int Da = a.upd ? a.D >> 1 : a.D, Ha = a.up ? a.H >> 1 : a.H, Wa = a.up ? a.W >> 1 : a.W;
     const int nca8 = a.Ca >> 3;
     constexpr int nchunk = NC8 * SROWS;
@@ -160,7 +181,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs2_kernel(const __grid_con
         }
       }
       for (int ds = s_begin; ds < s_end; ++ds) {
+        if (warp == 6) VXM_TR(2, ltr, 0);
         mbar_wait(&empty[slot], lphase);
+        if (warp == 6) VXM_TR(2, ltr, 1);
         uint8_t* slab = s_slab + (size_t)slot * slab_bytes;
         const bool dok = ds >= 0 && ds < a.D;
         const __nv_bfloat16* baseA = a.xa ? a.xa + (((size_t)b * Da + (dok ? (a.upd ? ds >> 1 : ds) : 0)) * Ha * Wa) * a.Ca : nullptr;
@@ -186,6 +209,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs2_kernel(const __grid_con
           }
           cp_async_arrive_noinc(&full[slot]);
         }
+        if (warp == 6) VXM_TR(2, ltr, 2);
+        ++ltr;
         if (++slot == (uint32_t)NSLOT) { slot = 0; lphase ^= 1; }
       }
     }
@@ -224,7 +249,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs2_kernel(const __grid_con
       for (int j = 0; j < nd; ++j) {
         const bool mine = (t & 1u) == me;
         if (mine) {
+          VXM_TR(me, t >> 1, 0);
           observe(gbase + (uint32_t)j + (KD == 3 ? 2u : 0u));
+          VXM_TR(me, t >> 1, 1);
           tc_fence_after();
           uint64_t adesc0_kd[KD], adesc1_kd[KD];
           {
@@ -243,6 +270,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs2_kernel(const __grid_con
               mbar_wait(&tempty[me * MAXACC + acc], (phbits >> acc) & 1u);
               phbits ^= 1u << acc;
             }
+            VXM_TR(me, t >> 1, 2 + 2 * hb);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + acc * (uint32_t)NN;
             if (elect_one()) {
@@ -274,6 +302,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs2_kernel(const __grid_con
               }
             }
             __syncwarp();
+            VXM_TR(me, t >> 1, 3 + 2 * hb);
           }
         } else if (KD == 1) {
           observe(gbase + (uint32_t)j);           // 2-D: a slab has one reader; the other issuer still observes and releases it
@@ -282,7 +311,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs2_kernel(const __grid_con
         }
         hslot = next_slot(hslot);
         ++t;
-        acc0 += 2 % NACC;
+        acc0 += 2;
         if (acc0 >= (uint32_t)NACC) acc0 -= NACC;
       }
       if (KD == 3) {
@@ -309,6 +338,103 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs2_kernel(const __grid_con
     uint32_t turn = 0, tphase = 0;   // accumulator counter % NACC; phase of this group's tfull barrier
     uint32_t ev = 0;                 // global event counter (2 * step + tile half)
     const int wq = warp & 3;
+    if constexpr (EPI != 0) {
+      const float slope = a.slope;
+      [[maybe_unused]] float bs[COUT];
+      if constexpr (EPI == 1) {
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) bs[c] = a.bias ? __ldg(a.bias + c) : 0.f;
+      }
+      const uint32_t tlane = tmem_base + ((uint32_t)(wq * 32) << 16);
+      uint32_t etr = 0;
+      const size_t slice = (size_t)a.H * a.W * COUT;            // elements per output slice
+      for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+        const int wt = item % a.tiles_w, ht = (item / a.tiles_w) % a.tiles_h;
+        const int ch = (item / HW_tiles) % a.nchunks, b = item / (HW_tiles * a.nchunks);
+        const int w = wt * WUSE - 1 + lane, d0 = ch * a.dchunk, d1 = min(d0 + a.dchunk, a.D);
+        const bool wok = lane >= 1 && lane <= WUSE && w < a.W;
+        bool ok[NH];
+        size_t off[NH];                                          // element offset of this lane's voxel in slice d0
+#pragma unroll
+        for (int hb = 0; hb < NH; ++hb) {
+          const int h = ht * HT + hb * 4 + wq;
+          ok[hb] = wok && h < a.H;
+          off[hb] = ((((size_t)b * a.D + d0) * a.H + h) * a.W + w) * COUT;
+        }
+        for (int d = d0; d < d1; ++d) {
+#pragma unroll
+          for (int hb = 0; hb < NH; ++hb) {
+            const uint32_t acc = turn;                           // accumulator of this event: (event counter) % NACC
+            const bool mine = (int)turn == grp || (int)turn == grp + 3;
+            if (++turn == (uint32_t)NACC) turn = 0;
+            ++ev;
+            const size_t o = off[hb];
+            off[hb] += slice;
+            if (!mine) continue;
+            const uint32_t taddr = tlane + acc * (uint32_t)NN;
+            const bool valid = ok[hb];
+            [[maybe_unused]] uint4 mreg[COUT / 8];
+            if constexpr (EPI == 2) {
+              if (valid) {
+#pragma unroll
+                for (int q = 0; q < COUT / 8; ++q) mreg[q] = __ldg(reinterpret_cast<const uint4*>(a.mask + o) + q);
+              }
+            }
+            if (wq == 0) VXM_TR(3 + grp, etr, 0);
+            mbar_wait(&tfull[acc], (tphase >> acc) & 1u);
+            if (wq == 0) VXM_TR(3 + grp, etr, 1);
+            tphase ^= 1u << acc;
+            tc_fence_after();
+#pragma unroll
+            for (int c0 = 0; c0 < COUT; c0 += 16) {
+              uint32_t r0[16], r1[16], r2[16];
+              tmem_ld16(taddr + c0, r0);
+              tmem_ld16(taddr + COUT + c0, r1);
+              tmem_ld16(taddr + 2 * COUT + c0, r2);
+              tmem_ld_wait();
+              if (c0 + 16 >= COUT) {          // last TMEM read of this accumulator: hand it to the issuer of event e + NACC
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[((((ev - 1u) + (uint32_t)NACC) >> 1) & 1u) * MAXACC + acc]);
+                if (wq == 0) VXM_TR(3 + grp, etr, 2);
+              }
+              float v[16];
+#pragma unroll
+              for (int c = 0; c < 16; ++c) {
+                const float p0 = __shfl_up_sync(0xffffffffu, __uint_as_float(r0[c]), 1);
+                const float p2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[c]), 1);
+                v[c] = (p0 + __uint_as_float(r1[c])) + p2;      // out[w'] = P0[w'-1] + P1[w'] + P2[w'+1]
+              }
+              if constexpr (EPI == 1) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                  const float x = v[c] + bs[c0 + c];
+                  v[c] = fmaxf(x, x * slope);                    // LeakyReLU for 0 <= slope <= 1
+                }
+              } else {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                  const uint4 m4 = mreg[c0 / 8 + q];
+                  const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {                  // sign bits of the saved bf16 activations
+                    if (mw[e] & 0x8000u) v[q * 8 + 2 * e] *= slope;
+                    if (mw[e] & 0x80000000u) v[q * 8 + 2 * e + 1] *= slope;
+                  }
+                }
+              }
+              if (valid) {
+                uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + o + c0);
+                op[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                op[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+              }
+            }
+            if (wq == 0) VXM_TR(3 + grp, etr, 3);
+            ++etr;
+          }
+        }
+      }
+    } else {
     const size_t HWp = (size_t)a.H * a.W;
     constexpr int NBR = COUT <= 32 ? COUT : 1;     // bias kept in registers for the (forward) layer widths
     float biasr[NBR];
@@ -322,15 +448,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs2_kernel(const __grid_con
       for (int d = d0; d < d1; ++d) {
 #pragma unroll
         for (int hb = 0; hb < NH; ++hb) {
+        uint32_t eacc;
         {
-          const bool mine = (int)turn == grp;
+          eacc = turn;
+          const bool mine = (int)turn == grp || (int)turn == grp + 3;
           if (++turn == (uint32_t)NACC) turn = 0;
           ++ev;
           if (!mine) continue;
         }
         const int h = ht * HT + hb * 4 + wq;
         const bool valid = lane >= 1 && lane <= WUSE && h < a.H && w < a.W;
-        const uint32_t acc = (uint32_t)grp;
+        const uint32_t acc = eacc;
         const size_t vox = (((size_t)b * a.D + d) * a.H + h) * a.W + w;
         // prefetch the LeakyReLU-derivative mask of this voxel before waiting for the tensor core
         uint4 mreg[COUT / 8];
@@ -339,8 +467,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs2_kernel(const __grid_con
           for (int q = 0; q < COUT / 8; ++q)
             if (q * 8 < a.Cout) mreg[q] = __ldg(reinterpret_cast<const uint4*>(a.mask + vox * a.Cout) + q);
         }
-        mbar_wait(&tfull[acc], tphase);
-        tphase ^= 1;
+        mbar_wait(&tfull[acc], (tphase >> acc) & 1u);
+        tphase ^= 1u << acc;
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * (uint32_t)NN;
         const int c1 = a.out2 ? a.csplit : a.Cout;          // channels [0,c1) -> out, [c1,Cout) -> out2
@@ -359,7 +487,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs2_kernel(const __grid_con
           }
           if (c0 + 16 >= COUT) {          // last TMEM read of this accumulator
             tc_fence_before();
-            mbar_arrive(&tempty[((((ev - 1u) + (uint32_t)NACC) >> 1) & 1u) * MAXACC + acc]);   // issuer of event e + NACC, e = ev - 1
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[((((ev - 1u) + (uint32_t)NACC) >> 1) & 1u) * MAXACC + acc]);   // issuer of event e + NACC, e = ev - 1
           }
           float v[16];
 #pragma unroll
@@ -407,6 +536,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs2_kernel(const __grid_con
         }
         }
       }
+    }
     }
   }
   tc_fence_before();
@@ -465,6 +595,10 @@ extern "C" int vxm_conv3d_tcs2_fwd(const void* xa, const void* xb, const void* w
   {
     const char* e = getenv("VXM_B200_TCS_DBG");
     a.dbg = e ? atoi(e) : 0;
+    const char* tr = getenv("VXM_B200_TCS_TRACE");
+    a.trace = tr ? (unsigned long long*)strtoull(tr, nullptr, 10) : nullptr;
+    const char* na = getenv("VXM_B200_TCS_NACC");     // "3": A/B switch
+    a.nacc = (6 * 3 * coutp <= 512 && !(na && na[0] == '3')) ? 6 : 3;
     // TMA plan: a channel group whose channels all come from one source tensor read at its own resolution (VXM_B200_TMA=0: none)
     a.tma_mask = 0; a.tc0[0] = a.tc0[1] = 0;
     const char* t = getenv("VXM_B200_TMA");
@@ -483,10 +617,24 @@ extern "C" int vxm_conv3d_tcs2_fwd(const void* xa, const void* xb, const void* w
       }
     }
   }
+  // epilogue specialisation (see the kernel): 3-D, bf16 channels-last output with all padded channels real, no channel split
+  int epi = 0;
+  {
+    const char* e = getenv("VXM_B200_TCS_EPI");       // "0": generic epilogue everywhere (A/B switch)
+    const bool plain = kd == 3 && out_mode == 0 && !out2 && Cout == coutp && !(e && e[0] == '0');
+    if (plain && !mask && slope >= 0.f && slope <= 1.f) epi = 1;
+    else if (plain && mask && !bias) epi = 2;
+  }
+#define VXM_TCS2_LAUNCH_E(KD_, G0_, G1_, CO_, E_)                                                                              \
+  do {                                                                                                                        \
+    VXM_CUDA(cudaFuncSetAttribute(conv_tcs2_kernel<KD_, G0_, G1_, CO_, 8, E_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    conv_tcs2_kernel<KD_, G0_, G1_, CO_, 8, E_><<<grid, NTHREADS, smem, st>>>(a);                                               \
+  } while (0)
 #define VXM_TCS2_LAUNCH(KD_, G0_, G1_, CO_)                                                                                    \
   do {                                                                                                                        \
-    VXM_CUDA(cudaFuncSetAttribute(conv_tcs2_kernel<KD_, G0_, G1_, CO_, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    conv_tcs2_kernel<KD_, G0_, G1_, CO_, 8><<<grid, NTHREADS, smem, st>>>(a);                                                   \
+    if (KD_ == 3 && epi == 1) VXM_TCS2_LAUNCH_E(3, G0_, G1_, CO_, 1);                                                          \
+    else if (KD_ == 3 && epi == 2) VXM_TCS2_LAUNCH_E(3, G0_, G1_, CO_, 2);                                                     \
+    else VXM_TCS2_LAUNCH_E(KD_, G0_, G1_, CO_, 0);                                                                             \
   } while (0)
 #define VXM_TCS2_G(KD_, CO_)                                                                                                  \
   do {                                                                                                                        \

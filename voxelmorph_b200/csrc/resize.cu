@@ -229,13 +229,15 @@ __global__ void __launch_bounds__(256) resize_bwd_march_kernel(const float* __re
   while (zcur < iz_end) flush();
 }
 
-// Tiled adjoint for upsampling ratios (the backward of `fullsize`, reading the FULL-resolution gradient): the marching
-// kernel's lanes read that gradient with stride ~2 (~3 L1 wavefronts per load, 16-25 loads per plane and channel) and are
-// bound by L1 wavefronts (143 us at 160x192x224).  Here a CTA stages the output-gradient region its 4 x 8 x 32 input tile
-// touches in shared memory with coalesced row loads, then applies the three 1-D adjoints separably in shared memory
-// (x: lane = input column with its list in registers; y: warp = input row; z: 4 slices), ~45 shared loads per result.
-constexpr int RT_X = 32, RT_Y = 8, RT_Z = 4, RT_MX = 72, RT_MY = 22, RT_MZ = 12;
-constexpr size_t RT_SMEM = (size_t)(RT_MZ * RT_MY * RT_MX + RT_MZ * RT_MY * RT_X) * sizeof(float);
+// Upsampling adjoint (the backward of `fullsize`, reading the FULL-resolution gradient), "shared-memory column marching":
+// the plain marching kernel's lanes read the gradient with stride ~2 and ~25 loads per plane and channel (L1-wavefront
+// bound).  Here a CTA owns a 32 x 8 (x, y) tile of the INPUT grid and a chunk of its z range, and walks the output planes
+// that touch the chunk.  Per plane the rows the tile touches (<= 22 rows of <= 72 columns per channel) are fetched with
+// coalesced row loads — prefetched into registers one plane ahead — and staged in shared memory; the x adjoint (lane =
+// input column, list in registers) and the y adjoint (warp = input row) are applied there, and the z adjoint runs in two
+// register accumulators exactly as in the marching kernel.  Same lists, same summation order per axis: deterministic.
+constexpr int RT_X = 32, RT_Y = 8, RT_MX = 72, RT_MY = 22;
+constexpr int RC_ZCHUNK = 8;
 
 __device__ __forceinline__ float adj_dot(const AdjList& L, const float* __restrict__ p, int stride) {
   float acc = 0.f;
@@ -245,64 +247,108 @@ __device__ __forceinline__ float adj_dot(const AdjList& L, const float* __restri
   return acc;
 }
 
-__global__ void __launch_bounds__(256, 2) resize_bwd_tile_kernel(const float* __restrict__ gout, float* __restrict__ gx, ResizeGeom g, int nzt) {
-  extern __shared__ __align__(16) float rsm[];
-  float* G = rsm;                                   // [EZ][EY][RT_MX]  staged output gradient
-  float* X1 = rsm + RT_MZ * RT_MY * RT_MX;          // [EZ][EY][32]     after the x adjoint
-  float* Y1 = rsm;                                  // [EZ][8][32]      after the y adjoint (reuses G)
-  __shared__ AdjList ends[6];                       // first / last list of the tile along x, y, z
-  __shared__ AdjList zl[RT_Z];
+template <int NC>
+__global__ void __launch_bounds__(256) resize_bwd_colsm_kernel(const float* __restrict__ gout, float* __restrict__ gx, ResizeGeom g) {
+  constexpr int RMAX = (NC * RT_MY + 7) / 8;          // rows per warp and plane
+  __shared__ float G[NC * RT_MY * RT_MX];            // staged rows of one output plane
+  __shared__ float X1[NC * RT_MY * RT_X];            // after the x adjoint
+  __shared__ AdjList ends[4];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int bx = blockIdx.x * RT_X, by = blockIdx.y * RT_Y;
-  const int bz = (blockIdx.z % nzt) * RT_Z, bc = blockIdx.z / nzt;
-  if (tid < 6) {
-    const AxisMap& m = tid < 2 ? g.mx : (tid < 4 ? g.my : g.mz);
-    const int b0 = tid < 2 ? bx : (tid < 4 ? by : bz), T = tid < 2 ? RT_X : (tid < 4 ? RT_Y : RT_Z);
+  const int zc = blockIdx.z % g.nzc, bc0 = (blockIdx.z / g.nzc) * NC;
+  if (tid < 4) {
+    const AxisMap& m = tid < 2 ? g.mx : g.my;
+    const int b0 = tid < 2 ? bx : by, T = tid < 2 ? RT_X : RT_Y;
     make_adj(m, (tid & 1) ? min(b0 + T - 1, m.in - 1) : b0, ends[tid]);
-  } else if (tid >= 32 && tid < 32 + RT_Z) {
-    const int iz = bz + (tid - 32);
-    if (iz < g.mz.in) make_adj(g.mz, iz, zl[tid - 32]); else zl[tid - 32].n = 0;
   }
   __syncthreads();
-  const int xlo = ends[0].lo, ylo = ends[2].lo, zlo = ends[4].lo;
-  const int EX = min(ends[1].lo + ends[1].n - xlo, RT_MX), EY = min(ends[3].lo + ends[3].n - ylo, RT_MY), EZ = min(ends[5].lo + ends[5].n - zlo, RT_MZ);
-  const size_t oHW = (size_t)g.my.out * g.mx.out, cout = oHW * g.mz.out;
-  const float* gb = gout + (size_t)bc * cout + (size_t)zlo * oHW + (size_t)ylo * g.mx.out + xlo;
-  for (int row = warp; row < EZ * EY; row += 8) {
-    const int z = row / EY, y = row - z * EY;
-    const float* src = gb + (size_t)z * oHW + (size_t)y * g.mx.out;
-    float* dst = G + (z * RT_MY + y) * RT_MX;
-    for (int x = lane; x < EX; x += 32) dst[x] = __ldg(src + x);
-  }
-  __syncthreads();
+  const int xlo = ends[0].lo, ylo = ends[2].lo;
+  const int EX = min(ends[1].lo + ends[1].n - xlo, RT_MX), EY = min(ends[3].lo + ends[3].n - ylo, RT_MY);
+  const int nrows = NC * EY;
   const int ix = bx + lane, iy = by + warp;
-  {
-    AdjList X;
-    if (ix < g.mx.in) make_adj(g.mx, ix, X); else { X.lo = xlo; X.n = 0; }
-    const int xo = X.lo - xlo;
-    for (int row = warp; row < EZ * EY; row += 8) {
-      const int z = row / EY, y = row - z * EY;
-      X1[(z * RT_MY + y) * RT_X + lane] = adj_dot(X, G + (z * RT_MY + y) * RT_MX + xo, 1);
-    }
-  }
-  __syncthreads();
-  {
-    AdjList Y;
-    if (iy < g.my.in) make_adj(g.my, iy, Y); else { Y.lo = ylo; Y.n = 0; }
-    const int yo = Y.lo - ylo;
-    for (int z = 0; z < EZ; ++z) Y1[(z * RT_Y + warp) * RT_X + lane] = adj_dot(Y, X1 + (z * RT_MY + yo) * RT_X + lane, RT_X);
-  }
-  __syncthreads();
-  if (ix < g.mx.in && iy < g.my.in) {
-    float* ob = gx + (((size_t)bc * g.mz.in + bz) * g.my.in + iy) * g.mx.in + ix;
+  AdjList X, Y;
+  if (ix < g.mx.in) make_adj(g.mx, ix, X); else { X.lo = xlo; X.n = 0; }
+  if (iy < g.my.in) make_adj(g.my, iy, Y); else { Y.lo = ylo; Y.n = 0; }
+  const int xo = X.lo - xlo, yo = Y.lo - ylo;
+  const size_t oHW = (size_t)g.my.out * g.mx.out, cout = oHW * g.mz.out;
+  const size_t iHW = (size_t)g.my.in * g.mx.in, cin = iHW * g.mz.in;
+  const float* gb = gout + (size_t)bc0 * cout + (size_t)ylo * g.mx.out + xlo;
+  float* ob = gx + (size_t)bc0 * cin + (size_t)iy * g.mx.in + ix;
+  const bool owner = ix < g.mx.in && iy < g.my.in;
+  const int iz_begin = zc * g.zchunk, iz_end = min(iz_begin + g.zchunk, g.mz.in);
+  int oz_lo, oz_hi, t;
+  adj_range(g.mz, iz_begin, oz_lo, t);
+  adj_range(g.mz, iz_end - 1, t, oz_hi);
+  // row r of a plane: channel r / EY, output row ylo + r % EY; this warp stages rows warp, warp + 8, ...
+  int roff[RMAX];
 #pragma unroll
-    for (int j = 0; j < RT_Z; ++j) {
-      if (bz + j < g.mz.in) {
-        const AdjList& Z = zl[j];
-        ob[(size_t)j * g.my.in * g.mx.in] = adj_dot(Z, Y1 + ((Z.lo - zlo) * RT_Y + warp) * RT_X + lane, RT_Y * RT_X) * g.scale;
+  for (int j = 0; j < RMAX; ++j) {
+    const int r = warp + 8 * j;
+    const int c = r / EY, y = r - c * EY;
+    roff[j] = r < nrows ? (int)((size_t)c * cout + (size_t)y * g.mx.out) : -1;     // < 2^31: checked on the host
+  }
+  float pre[RMAX][3];
+  auto fetch = [&](int oz) {
+    const float* pl = gb + (size_t)oz * oHW;
+#pragma unroll
+    for (int j = 0; j < RMAX; ++j) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int x = lane + 32 * q;
+        pre[j][q] = (roff[j] >= 0 && x < EX) ? __ldg(pl + roff[j] + x) : 0.f;
       }
     }
+  };
+  float A0[NC], A1[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) A0[c] = A1[c] = 0.f;
+  int zcur = iz_begin;           // A0 accumulates input slice zcur, A1 slice zcur + 1
+  auto flush = [&]() {
+    if (zcur < iz_end && owner) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) ob[(size_t)c * cin + (size_t)zcur * iHW] = A0[c] * g.scale;
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { A0[c] = A1[c]; A1[c] = 0.f; }
+    ++zcur;
+  };
+  // the planes that touch the chunk are a contiguous range: trim both ends (block-uniform)
+  while (oz_lo <= oz_hi) { int z0, z1; float a, b; src_index(g.mz, oz_lo, z0, z1, a, b); if (z1 < iz_begin) ++oz_lo; else break; }
+  while (oz_hi >= oz_lo) { int z0, z1; float a, b; src_index(g.mz, oz_hi, z0, z1, a, b); if (z0 >= iz_end) --oz_hi; else break; }
+  if (oz_lo <= oz_hi) fetch(oz_lo);
+  for (int oz = oz_lo; oz <= oz_hi; ++oz) {
+    int z0, z1;
+    float lz0, lz1;
+    src_index(g.mz, oz, z0, z1, lz0, lz1);
+#pragma unroll
+    for (int j = 0; j < RMAX; ++j) {
+      const int r = warp + 8 * j;
+      if (r < nrows) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const int x = lane + 32 * q;
+          if (x < RT_MX) G[r * RT_MX + x] = pre[j][q];
+        }
+      }
+    }
+    __syncthreads();
+    if (oz < oz_hi) fetch(oz + 1);                 // next plane's loads fly during this plane's arithmetic
+#pragma unroll
+    for (int j = 0; j < RMAX; ++j) {
+      const int r = warp + 8 * j;
+      if (r < nrows) X1[r * RT_X + lane] = adj_dot(X, G + r * RT_MX + xo, 1);
+    }
+    __syncthreads();
+    while (zcur < z0 && zcur < iz_end) flush();
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const float R = adj_dot(Y, X1 + (c * EY + yo) * RT_X + lane, RT_X);
+      if (z0 == zcur) A0[c] += lz0 * R;
+      if (z1 == zcur) A0[c] += lz1 * R;
+      else if (z1 == zcur + 1) A1[c] += lz1 * R;
+    }
   }
+  while (zcur < iz_end) flush();
 }
 
 // largest number of outputs any T-wide input tile touches along one axis (same fp32 index arithmetic as the device)
@@ -399,13 +445,15 @@ extern "C" int vxm_resize_bwd(const float* grad_out, float* grad_x, int B, int C
   auto fits = [](const AxisMap& m) { return m.in == m.out || (m.ratio > 0.f && 2.0f / m.ratio + 1.5f <= (float)ADJ_L); };
   const char* ek = getenv("VXM_B200_RESIZE_BWD");      // "march": A/B switch
   const bool up = Do > Di && Ho > Hi && Wo > Wi && !(ek && ek[0] == 'm');
-  if (up && fits(g.mz) && fits(g.my) && fits(g.mx) && host_tile_extent(g.mx, RT_X) <= RT_MX && host_tile_extent(g.my, RT_Y) <= RT_MY &&
-      host_tile_extent(g.mz, RT_Z) <= RT_MZ) {
-    const int nzt = (Di + RT_Z - 1) / RT_Z;
-    VXM_REQUIRE((size_t)nzt * B * C <= 65535u, "resize_bwd: B*C*D exceeds the launch grid limit");
-    VXM_CUDA(cudaFuncSetAttribute(resize_bwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM));
-    dim3 grid((Wi + RT_X - 1) / RT_X, (Hi + RT_Y - 1) / RT_Y, nzt * B * C);
-    resize_bwd_tile_kernel<<<grid, 256, RT_SMEM, st>>>(grad_out, grad_x, g, nzt);
+  if (up && fits(g.mz) && fits(g.my) && fits(g.mx) && host_tile_extent(g.mx, RT_X) <= RT_MX && host_tile_extent(g.my, RT_Y) <= RT_MY) {
+    const int nc = (B * C) % 3 == 0 ? 3 : 1;
+    g.zchunk = RC_ZCHUNK;
+    g.nzc = (Di + RC_ZCHUNK - 1) / RC_ZCHUNK;
+    VXM_REQUIRE((size_t)g.nzc * (B * C / nc) <= 65535u, "resize_bwd: B*C*D exceeds the launch grid limit");
+    VXM_REQUIRE((size_t)nc * Do * Ho * Wo < (1ull << 31), "resize_bwd: gradient exceeds 2^31 elements per channel group");
+    dim3 grid((Wi + RT_X - 1) / RT_X, (Hi + RT_Y - 1) / RT_Y, g.nzc * (B * C / nc));
+    if (nc == 3) resize_bwd_colsm_kernel<3><<<grid, 256, 0, st>>>(grad_out, grad_x, g);
+    else resize_bwd_colsm_kernel<1><<<grid, 256, 0, st>>>(grad_out, grad_x, g);
   } else if (fits(g.mz) && fits(g.my) && fits(g.mx)) {
     const int nc = channels_per_thread(B * C);
     dim3 block(32, 8, 1), grid((Wi + 31) / 32, (Hi + 7) / 8, g.nzc * (B * C / nc));
