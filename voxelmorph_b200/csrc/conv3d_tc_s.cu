@@ -60,7 +60,10 @@ __device__ __forceinline__ uint64_t make_desc_kmajor_swz(uint32_t saddr, uint32_
 // overhead that bounds the thin layers and cutting the halo re-reads from 1.5x to 1.25x.
 // ACC: the split-precision epilogue (acc_in / out_mode 2, 3) is compiled in; the plain kernels (ACC = false) keep the
 // round-1 epilogue — with the extra live registers the 32-channel variants spilled and lost up to 1.8x.
-template <int KD, int G0, int G1, int COUT, int HT, bool ACC>
+// EPI: epilogue specialisation (see conv3d_tc_s2.cu).  0 = generic run-time epilogue; 1 = forward (bias + LeakyReLU with
+// 0 <= slope <= 1, bf16 channels-last, all COUT channels real); 2 = dgrad (LeakyReLU derivative from the saved activation);
+// 3 = raw sums with an optional channel split at a multiple of 16 (single-pass dgrad of a concat layer).
+template <int KD, int G0, int G1, int COUT, int HT, bool ACC, int EPI>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const __grid_constant__ ConvSArgs a) {
   constexpr int SROWS = (HT + 2) * WT;
   constexpr int NH = HT / 4;
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const __grid_cons
   const bool all_tma = tma0 && (G1 == 0 || tma1);        // no cp.async traffic at all: one producer thread
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSLOT; ++i) { mbar_init(&full[i], all_tma ? 1 : NLOADER); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < NACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }     // one arrival per epilogue warp
     mbar_init(wbar, 1);
     fence_barrier_init();
   }
@@ -261,6 +264,98 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const __grid_cons
     const int grp = warp >= 12 ? 2 : (warp >= 8 ? 1 : 0);
     uint32_t turn = 0, tphase = 0;   // accumulator counter % NACC; phase of this group's tfull barrier
     const int wq = warp & 3;
+    if constexpr (EPI != 0) {
+      const float slope = a.slope;
+      [[maybe_unused]] float bs[EPI == 1 ? COUT : 1];
+      if constexpr (EPI == 1) {
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) bs[c] = a.bias ? __ldg(a.bias + c) : 0.f;
+      }
+      const uint32_t acc = (uint32_t)grp;
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * (uint32_t)NN;
+      const int c1 = (EPI == 3 && a.out2) ? a.csplit : COUT;       // channels [0, c1) -> out, [c1, COUT) -> out2
+      const size_t HWp = (size_t)a.H * a.W;
+      for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+        const int wt = item % a.tiles_w, ht = (item / a.tiles_w) % a.tiles_h;
+        const int ch = (item / HW_tiles) % a.nchunks, b = item / (HW_tiles * a.nchunks);
+        const int w = wt * WUSE - 1 + lane, d0 = ch * a.dchunk, d1 = min(d0 + a.dchunk, a.D);
+        const bool wok = lane >= 1 && lane <= WUSE && w < a.W;
+        bool ok[NH];
+        size_t vx[NH];                                           // voxel index of this lane in slice d0
+#pragma unroll
+        for (int hb = 0; hb < NH; ++hb) {
+          const int h = ht * HT + hb * 4 + wq;
+          ok[hb] = wok && h < a.H;
+          vx[hb] = (((size_t)b * a.D + d0) * a.H + h) * a.W + w;
+        }
+        for (int d = d0; d < d1; ++d) {
+#pragma unroll
+          for (int hb = 0; hb < NH; ++hb) {
+            const bool mine = (int)turn == grp;
+            if (++turn == (uint32_t)NACC) turn = 0;
+            const size_t vox = vx[hb];
+            vx[hb] += HWp;
+            if (!mine) continue;
+            const bool valid = ok[hb];
+            [[maybe_unused]] uint4 mreg[EPI == 2 ? COUT / 8 : 1];
+            if constexpr (EPI == 2) {
+              if (valid) {
+#pragma unroll
+                for (int q = 0; q < COUT / 8; ++q) mreg[q] = __ldg(reinterpret_cast<const uint4*>(a.mask + vox * COUT) + q);
+              }
+            }
+            mbar_wait(&tfull[acc], tphase);
+            tphase ^= 1;
+            tc_fence_after();
+#pragma unroll
+            for (int c0 = 0; c0 < COUT; c0 += 16) {
+              uint32_t r0[16], r1[16], r2[16];
+              tmem_ld16(taddr + c0, r0);
+              tmem_ld16(taddr + COUT + c0, r1);
+              tmem_ld16(taddr + 2 * COUT + c0, r2);
+              tmem_ld_wait();
+              if (c0 + 16 >= COUT) {          // last TMEM read of this accumulator
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+              }
+              float v[16];
+#pragma unroll
+              for (int c = 0; c < 16; ++c) {
+                const float p0 = __shfl_up_sync(0xffffffffu, __uint_as_float(r0[c]), 1);
+                const float p2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[c]), 1);
+                v[c] = (p0 + __uint_as_float(r1[c])) + p2;      // out[w'] = P0[w'-1] + P1[w'] + P2[w'+1]
+              }
+              if constexpr (EPI == 1) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                  const float x = v[c] + bs[c0 + c];
+                  v[c] = fmaxf(x, x * slope);                    // LeakyReLU for 0 <= slope <= 1
+                }
+              } else if constexpr (EPI == 2) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                  const uint4 m4 = mreg[c0 / 8 + q];
+                  const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {                  // sign bits of the saved bf16 activations
+                    if (mw[e] & 0x8000u) v[q * 8 + 2 * e] *= slope;
+                    if (mw[e] & 0x80000000u) v[q * 8 + 2 * e + 1] *= slope;
+                  }
+                }
+              }
+              if (valid) {
+                __nv_bfloat16* dst = (EPI == 3 && c0 >= c1) ? reinterpret_cast<__nv_bfloat16*>(a.out2) + vox * (COUT - c1) + (c0 - c1)
+                                                            : reinterpret_cast<__nv_bfloat16*>(a.out) + vox * c1 + c0;
+                uint4* op = reinterpret_cast<uint4*>(dst);
+                op[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                op[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+              }
+            }
+          }
+        }
+      }
+    } else {
     const size_t HWp = (size_t)a.H * a.W;
     constexpr int NBR = COUT <= 32 ? COUT : 1;     // bias kept in registers for the (forward) layer widths
     float biasr[NBR];
@@ -313,7 +408,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const __grid_cons
           tmem_ld_wait();
           if (c0 + 16 >= COUT) {          // last TMEM read of this accumulator
             tc_fence_before();
-            mbar_arrive(&tempty[acc]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
           }
           float v[16];
 #pragma unroll
@@ -397,6 +493,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const __grid_cons
         }
         }
       }
+    }
     }
   }
   tc_fence_before();
@@ -629,15 +726,27 @@ static int conv_tcs_launch(const void* xa, const void* xb, const void* wpk, cons
   cudaStream_t st = as_stream(stream);
   if (plan_tma(a, g0, g1, HTv) != 0) return VXM_ERR_CUDA;
   const bool acc_epi = acc_in != nullptr || out_mode >= 2;
+  // epilogue specialisation: 3-D, bf16 channels-last output, every padded channel real
+  int epi = 0;
+  {
+    const char* e = getenv("VXM_B200_TCS_EPI");       // "0": generic epilogue everywhere (A/B switch)
+    const bool plain = kd == 3 && out_mode == 0 && !acc_epi && Cout == coutp && !(e && e[0] == '0');
+    if (plain && !out2 && !mask && slope >= 0.f && slope <= 1.f) epi = 1;
+    else if (plain && !out2 && mask && !bias) epi = 2;
+    else if (plain && !mask && !bias && slope < 0.f && (!out2 || csplit % 16 == 0)) epi = 3;
+  }
+#define VXM_TCS_LAUNCH_E(KD_, G0_, G1_, CO_, HT_, ACC_, E_)                                                                       \
+  do {                                                                                                                            \
+    VXM_CUDA(cudaFuncSetAttribute(conv_tcs_kernel<KD_, G0_, G1_, CO_, HT_, ACC_, E_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    conv_tcs_kernel<KD_, G0_, G1_, CO_, HT_, ACC_, E_><<<grid, NTHREADS, smem, st>>>(a);                                          \
+  } while (0)
 #define VXM_TCS_LAUNCH(KD_, G0_, G1_, CO_, HT_)                                                                                   \
   do {                                                                                                                            \
-    if (acc_epi) {                                                                                                                \
-      VXM_CUDA(cudaFuncSetAttribute(conv_tcs_kernel<KD_, G0_, G1_, CO_, HT_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      conv_tcs_kernel<KD_, G0_, G1_, CO_, HT_, true><<<grid, NTHREADS, smem, st>>>(a);                                            \
-    } else {                                                                                                                      \
-      VXM_CUDA(cudaFuncSetAttribute(conv_tcs_kernel<KD_, G0_, G1_, CO_, HT_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      conv_tcs_kernel<KD_, G0_, G1_, CO_, HT_, false><<<grid, NTHREADS, smem, st>>>(a);                                           \
-    }                                                                                                                             \
+    if (acc_epi) VXM_TCS_LAUNCH_E(KD_, G0_, G1_, CO_, HT_, true, 0);                                                              \
+    else if (KD_ == 3 && epi == 1) VXM_TCS_LAUNCH_E(3, G0_, G1_, CO_, HT_, false, 1);                                             \
+    else if (KD_ == 3 && epi == 2) VXM_TCS_LAUNCH_E(3, G0_, G1_, CO_, HT_, false, 2);                                             \
+    else if (KD_ == 3 && epi == 3) VXM_TCS_LAUNCH_E(3, G0_, G1_, CO_, HT_, false, 3);                                             \
+    else VXM_TCS_LAUNCH_E(KD_, G0_, G1_, CO_, HT_, false, 0);                                                                     \
   } while (0)
 #define VXM_TCS_G8(KD_, CO_)                                                  \
   do {                                                                        \
