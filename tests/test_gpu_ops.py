@@ -393,3 +393,27 @@ def test_adam_parity(vxm, cuda):
         mopt.step()
         for p, q in zip(ref, mine):
             assert rel_err(q.detach().cpu().numpy(), p.detach().numpy()) <= 1e-6, step
+
+
+def test_resize_upsampling_adjoint_kernels_agree(vxm, cuda, monkeypatch):
+    """The shared-memory column-marching adjoint (default for x2 upsampling) against the plain marching kernel and fp64 autograd,
+    on a ragged size whose tiles are partial on every axis."""
+    from voxelmorph_b200 import _lib
+    lib = _lib.load()
+    Di, Hi, Wi = 21, 27, 45
+    Do, Ho, Wo = 42, 54, 90
+    g = torch.Generator().manual_seed(5)
+    go = torch.randn((1, 3, Do, Ho, Wo), generator=g).to(cuda)
+    outs = {}
+    for mode in ("", "march"):
+        if mode:
+            monkeypatch.setenv("VXM_B200_RESIZE_BWD", mode)
+        gx = torch.empty((1, 3, Di, Hi, Wi), device=cuda)
+        assert lib.vxm_resize_bwd(_lib.ptr(go), _lib.ptr(gx), 1, 3, Di, Hi, Wi, Do, Ho, Wo, 2.0, 1.0, _lib.stream_ptr()) == 0, _lib.last_error()
+        outs[mode] = gx.cpu()
+    x = torch.zeros((1, 3, Di, Hi, Wi), dtype=torch.float64, requires_grad=True)
+    y = torch.nn.functional.interpolate(x * 2.0, size=(Do, Ho, Wo), mode="trilinear", align_corners=True)
+    (y * go.cpu().double()).sum().backward()
+    for mode, v in outs.items():
+        assert rel_err(v.numpy(), x.grad.numpy()) <= 2e-6, mode
+    assert rel_err(outs[""].numpy(), outs["march"].numpy()) <= 1e-6

@@ -263,3 +263,46 @@ def test_tct_cin64(tc, cuda, variant):
     wpk, cp = tc.pack_weights_t(w.to(cuda), variant=variant)
     out = tc.conv_fwd_t(tc.to_ndhwc_bf16(xa.to(cuda)), tc.to_ndhwc_bf16(xb.to(cuda)), wpk, cp, None, 32, 3, up=True, slope=0.2)
     assert rel_err(tc.from_ndhwc(out).cpu(), ref) <= 1e-2
+
+
+# ---- round 2: TMA tile staging and the specialised epilogues are pure re-implementations: results must not change ----
+
+@pytest.mark.parametrize("shape,Ca,Cb,up,Cout,mode", [
+    ((12, 24, 70), 16, 0, False, 16, "fwd"),      # one channel group, tensor copy only (conv_tcs2, forward epilogue)
+    ((12, 24, 70), 32, 16, True, 32, "fwd"),      # upsampled group on cp.async + skip group by tensor copy (conv_tcs)
+    ((10, 20, 40), 16, 0, False, 32, "dgrad"),    # dgrad epilogue (mask)
+    ((10, 20, 40), 32, 0, False, 48, "split"),    # raw + channel split epilogue
+    ((9, 13, 35), 32, 0, False, 16, "fwd"),       # ragged sizes: out-of-bounds fill on every side
+])
+def test_tma_and_lean_epilogue_match_reference_paths(tc, cuda, monkeypatch, shape, Ca, Cb, up, Cout, mode):
+    g = torch.Generator().manual_seed(77)
+    D, H, W = shape
+    ashape = (D // 2, H // 2, W // 2) if up else shape
+    if up:
+        shape = (ashape[0] * 2, ashape[1] * 2, ashape[2] * 2)
+    xa = tc.to_ndhwc_bf16(torch.randn((2, Ca) + ashape, generator=g).to(cuda))
+    xb = tc.to_ndhwc_bf16(torch.randn((2, Cb) + shape, generator=g).to(cuda)) if Cb else None
+    if mode == "fwd":
+        w = torch.randn((Cout, Ca + Cb, 3, 3, 3), generator=g).to(cuda) * 0.1
+        b = torch.randn(Cout, generator=g).to(cuda)
+        wpk, cp = tc.pack_weights_t(w, variant="s")
+        run = lambda: tc.conv_fwd_t(xa, xb, wpk, cp, b, Cout, 3, up=up, slope=0.2)
+    else:
+        w = torch.randn((Ca, Cout, 3, 3, 3), generator=g).to(cuda) * 0.1       # dgrad of a Cout -> Ca layer: produces Cout channels
+        wpk, cp = tc.pack_weights_t(w, transposed=True, variant="s")
+        if mode == "dgrad":
+            m = tc.to_ndhwc_bf16(torch.randn((2, Cout) + shape, generator=g).to(cuda))
+            run = lambda: tc.conv_fwd_t(xa, None, wpk, cp, None, Cout, 3, slope=0.2, mask=m)
+        else:
+            run = lambda: torch.cat(tc.conv_fwd_t(xa, None, wpk, cp, None, Cout, 3, split=32), dim=-1)
+    outs = {}
+    for tma in ("1", "0"):
+        for epi in ("1", "0"):
+            monkeypatch.setenv("VXM_B200_TMA", tma)
+            monkeypatch.setenv("VXM_B200_TCS_EPI", epi)
+            outs[(tma, epi)] = run().float().cpu()
+    torch.cuda.synchronize()
+    ref = outs[("0", "0")]
+    assert torch.isfinite(ref).all() and float(ref.abs().max()) > 0
+    for k, v in outs.items():
+        assert torch.equal(v, ref), k      # same MMAs in the same order, same fp32 epilogue arithmetic: bit-identical

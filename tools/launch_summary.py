@@ -1,10 +1,11 @@
 """Aggregate an ncu launch list (--metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv) into the
 per-step table of profiles/: one step = the launches between the last two `adam_dev_kernel` launches.
-Usage: python tools/launch_summary.py launches.csv "<command line>" "<timed ms per step>" > profiles/x.md ; also writes the traffic json
-when a 4th argument names it."""
+Usage: python tools/launch_summary.py launches.csv "<command line>" "<timed ms per step>" [traffic.json [title]] > profiles/x.md ;
+the traffic json (stamped with the hash of the convolution sources) is what bench.py reports as roofline.traffic."""
 import csv, sys, json, collections, re
 
 path, cmdline, timed = sys.argv[1], sys.argv[2], sys.argv[3]
+title = sys.argv[5] if len(sys.argv) > 5 else "one training step, per-kernel device time and DRAM traffic (ncu)"
 rows = [r for r in csv.reader(open(path)) if len(r) >= 15 and r[0].isdigit()]
 launch = collections.OrderedDict()
 for r in rows:
@@ -37,7 +38,7 @@ for x in step:
 conv = [x for x in step if re.search(r"conv_tc|wgrad|pack_weights", x["name"])]
 conv_us = sum(x["us"] for x in conv)
 conv_bytes = sum(x.get("rd", 0) + x.get("wr", 0) for x in conv if re.search(r"conv_tc\w*_kernel|wgrad\w*_kernel", x["name"]) and "reduce" not in x["name"])
-print("# Round 1 (final state) — one training step, per-kernel device time and DRAM traffic (ncu)\n")
+print("# %s\n" % title)
 print("Command (gpurun, 1x B200): `%s`\n" % cmdline)
 print("bf16 tensor-core engine, eager launches (no CUDA graph) so that every kernel is visible.  ncu serialises launches and runs")
 print("them cold: read SHARES, not absolute times (the timed, graph-replayed bench step is %s ms)." % timed)
@@ -51,6 +52,9 @@ print("## Every launch of that step, in order\n\n| # | kernel | grid | time (us)
 for i, x in enumerate(step):
     print("| %d | `%s` | %s | %.1f | %.1f |" % (i, short(x["name"])[:80], x["grid"], x["us"], (x.get("rd", 0) + x.get("wr", 0)) / 1e6))
 if len(sys.argv) > 4:
-    json.dump({"conv_dram_mbytes_per_step": conv_bytes / 1e6,
-               "source": "profiles/r1_final_step_launches_summary.md (ncu dram__bytes_read.sum + dram__bytes_write.sum over the conv_tc*/wgrad* kernels of one step)"},
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench                      # the library sources this pass was captured from: bench.py refuses a stale figure
+    json.dump({"conv_dram_mbytes_per_step": conv_bytes / 1e6, "conv_source_sha": bench.conv_source_hash(),
+               "source": "%s (ncu dram__bytes_read.sum + dram__bytes_write.sum over the conv_tc*/wgrad* kernels of one step)" % os.path.basename(path)},
               open(sys.argv[4], "w"), indent=1)

@@ -9,6 +9,7 @@
 // Algorithmic bytes (fp32) per voxel per step: forward 4*nd read + 4*nd write;
 // backward 4*nd (v_k) + 4*nd (g_{k+1}) read + 4*nd (g_k) write.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "sampler.cuh"
 
@@ -239,25 +240,75 @@ __device__ __forceinline__ void corners_fast(float cz, float cy, float cx, const
   }
 }
 
-__device__ __forceinline__ float4 lerp4(const float4& a, const float4& b, float t) {
-  return make_float4(fmaf(t, b.x - a.x, a.x), fmaf(t, b.y - a.y, a.y), fmaf(t, b.z - a.z, a.z), 0.f);
+// Branch-free trilinear footprint of one sample point: clamped corner offsets (always loadable) and per-axis weights with
+// the zeros padding folded in (a corner outside the volume has weight 0), so interior and border voxels run the same code
+// and the gathers of several voxels can be in flight together.
+struct Foot {
+  int oz[2], oy[2], ox[2];     // clamped offsets of the two planes / rows / columns
+  float wz[2], wy[2], wx[2];   // (1 - t, t) or 0 where the plane / row / column lies outside the volume
+  float vz[2], vy[2], vx[2];   // 1 / 0 validity (the derivative of w with respect to the coordinate is -v[0], +v[1])
+  int key;                     // (z0 * H + y0) * W + x0 when all 8 corners are inside, else -1
+};
+__device__ __forceinline__ void footprint(float cz, float cy, float cx, const VecFast& g, Foot& f) {
+  const float fx = floorf(cx), fy = floorf(cy), fz = floorf(cz);
+  const int x0 = f2i(fx), y0 = f2i(fy), z0 = f2i(fz);
+  const float tx = cx - fx, ty = cy - fy, tz = cz - fz;
+  const bool bx0 = (unsigned)x0 < (unsigned)g.W, bx1 = (unsigned)(x0 + 1) < (unsigned)g.W;
+  const bool by0 = (unsigned)y0 < (unsigned)g.H, by1 = (unsigned)(y0 + 1) < (unsigned)g.H;
+  const bool bz0 = (unsigned)z0 < (unsigned)g.D, bz1 = (unsigned)(z0 + 1) < (unsigned)g.D;
+  f.vx[0] = bx0 ? 1.f : 0.f; f.vx[1] = bx1 ? 1.f : 0.f;
+  f.vy[0] = by0 ? 1.f : 0.f; f.vy[1] = by1 ? 1.f : 0.f;
+  f.vz[0] = bz0 ? 1.f : 0.f; f.vz[1] = bz1 ? 1.f : 0.f;
+  f.wx[0] = bx0 ? 1.f - tx : 0.f; f.wx[1] = bx1 ? tx : 0.f;
+  f.wy[0] = by0 ? 1.f - ty : 0.f; f.wy[1] = by1 ? ty : 0.f;
+  f.wz[0] = bz0 ? 1.f - tz : 0.f; f.wz[1] = bz1 ? tz : 0.f;
+  f.ox[0] = min(max(x0, 0), g.W - 1); f.ox[1] = min(max(x0 + 1, 0), g.W - 1);
+  f.oy[0] = min(max(y0, 0), g.H - 1) * g.W; f.oy[1] = min(max(y0 + 1, 0), g.H - 1) * g.W;
+  f.oz[0] = min(max(z0, 0), g.D - 1) * g.HW; f.oz[1] = min(max(z0 + 1, 0), g.D - 1) * g.HW;
+  f.key = (bx0 && bx1 && by0 && by1 && bz0 && bz1) ? (z0 * g.H + y0) * g.W + x0 : -1;
+}
+__device__ __forceinline__ void gather8(const float4* __restrict__ cb, const Foot& f, float4 (&u)[8]) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) u[k] = cb[f.oz[k >> 2] + f.oy[(k >> 1) & 1] + f.ox[k & 1]];
+}
+__device__ __forceinline__ float4 blend8(const Foot& f, const float4 (&u)[8]) {
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int zz = 0; zz < 2; ++zz) {
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int yy = 0; yy < 2; ++yy) {
+      const float4& a = u[zz * 4 + yy * 2], & b = u[zz * 4 + yy * 2 + 1];
+      const float qx = fmaf(f.wx[1], b.x, f.wx[0] * a.x), qy = fmaf(f.wx[1], b.y, f.wx[0] * a.y), qz = fmaf(f.wx[1], b.z, f.wx[0] * a.z);
+      p.x = fmaf(f.wy[yy], qx, p.x); p.y = fmaf(f.wy[yy], qy, p.y); p.z = fmaf(f.wy[yy], qz, p.z);
+    }
+    r.x = fmaf(f.wz[zz], p.x, r.x); r.y = fmaf(f.wz[zz], p.y, r.y); r.z = fmaf(f.wz[zz], p.z, r.z);
+  }
+  return r;
 }
 
+// Work decomposition of both fast kernels: the field is cut into 512-voxel blocks; CTA c owns the contiguous run of blocks
+// [c * nblk / grid, (c + 1) * nblk / grid) (so consecutive iterations of a CTA touch neighbouring rows: L1 reuse), and a thread
+// carries TWO voxels (blocks blk, blk + 1) per iteration with all 16 gathers in flight — at 16 warps per SM the kernel is bound by
+// the L2 round trip of its gathers otherwise (ncu: long scoreboard 45 %, issue slots 19 % busy, profiles/r2_memory_kernels.md).
 // SAVE: every intermediate field v_0 .. v_{n-1} is kept (states, for the backward); otherwise two buffers ping-pong
 template <bool SAVE>
 __global__ void __launch_bounds__(512) vecint_fwd_fast_kernel(const float* __restrict__ vel, float* __restrict__ out, float4* buf,
                                                               VecFast g, int nsteps, float scale) {
   cg::grid_group grid = cg::this_grid();
-  const int tid0 = blockIdx.x * blockDim.x + threadIdx.x;
-  const int stride = gridDim.x * blockDim.x;
+  const int nblk = (g.nvox + 511) >> 9;
+  const int blk0 = (int)((long long)blockIdx.x * nblk / gridDim.x), blk1 = (int)((long long)(blockIdx.x + 1) * nblk / gridDim.x);
   auto field = [&](int k) -> float4* { return buf + (size_t)(SAVE ? k : (k & 1)) * g.nvox; };
   {
     float4* f0 = field(0);
-    for (int q = tid0; q < g.nvox; q += stride) {
-      const int b = q / g.DHW;
-      const int p = q - b * g.DHW;
-      const float* vb = vel + (size_t)b * 3 * g.DHW + p;
-      f0[q] = make_float4(__ldg(vb) * scale, __ldg(vb + g.DHW) * scale, __ldg(vb + 2 * g.DHW) * scale, 0.f);
+    for (int blk = blk0; blk < blk1; ++blk) {
+      const int q = (blk << 9) + threadIdx.x;
+      if (q < g.nvox) {
+        const int b = q / g.DHW;
+        const int p = q - b * g.DHW;
+        const float* vb = vel + (size_t)b * 3 * g.DHW + p;
+        f0[q] = make_float4(__ldg(vb) * scale, __ldg(vb + g.DHW) * scale, __ldg(vb + 2 * g.DHW) * scale, 0.f);
+      }
     }
   }
   grid.sync();
@@ -265,41 +316,44 @@ __global__ void __launch_bounds__(512) vecint_fwd_fast_kernel(const float* __res
     const float4* __restrict__ cur = field(s);
     float4* __restrict__ nxt = field(s + 1);
     const bool last = s + 1 == nsteps;
-    // the voxel's own vector of the NEXT iteration is requested before this iteration's gathers: the dependent chain of an
-    // iteration is then one L2 round trip (the gathers), not two (own value -> coordinates -> gathers)
-    float4 v_next = tid0 < g.nvox ? cur[tid0] : make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int q = tid0; q < g.nvox; q += stride) {
-      const int t1 = fdiv(q, g.dW), x = q - t1 * g.W;
-      const int t2 = fdiv(t1, g.dH), y = t1 - t2 * g.H;
-      const int b = fdiv(t2, g.dD), z = t2 - b * g.D;
-      const float4* cb = cur + (size_t)b * g.DHW;
-      const float4 v = v_next;
-      if (q + stride < g.nvox) v_next = cur[q + stride];
-      Corner8 c;
-      corners_fast((float)z + v.x, (float)y + v.y, (float)x + v.z, g, c);
-      float4 r;
-      if (c.interior) {
-        const float4* s0 = cb + c.base;
-        const float4 a00 = s0[0], a01 = s0[1], a10 = s0[g.W], a11 = s0[g.W + 1];
-        const float4 b00 = s0[g.HW], b01 = s0[g.HW + 1], b10 = s0[g.HW + g.W], b11 = s0[g.HW + g.W + 1];
-        const float4 ra = lerp4(lerp4(a00, a01, c.tx), lerp4(a10, a11, c.tx), c.ty);
-        const float4 rb = lerp4(lerp4(b00, b01, c.tx), lerp4(b10, b11, c.tx), c.ty);
-        r = lerp4(ra, rb, c.tz);
-      } else {
-        r = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int blk = blk0; blk < blk1; blk += 2) {
+      int q[2];
+      bool has[2];
+      float4 v[2];
+      Foot f[2];
+      float4 u[2][8];
+      const float4* cb[2];
+      int bb[2];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float4 u = cb[c.off[k]];
-          r.x = fmaf(c.w[k], u.x, r.x); r.y = fmaf(c.w[k], u.y, r.y); r.z = fmaf(c.w[k], u.z, r.z);
-        }
+      for (int e = 0; e < 2; ++e) {
+        q[e] = ((blk + e) << 9) + threadIdx.x;
+        has[e] = blk + e < blk1 && q[e] < g.nvox;
+        if (!has[e]) q[e] = 0;
+        v[e] = cur[q[e]];
       }
-      const float4 o = make_float4(v.x + r.x, v.y + r.y, v.z + r.z, 0.f);
-      if (last) {
-        const int p = q - b * g.DHW;
-        float* ob = out + (size_t)b * 3 * g.DHW + p;
-        ob[0] = o.x; ob[g.DHW] = o.y; ob[2 * g.DHW] = o.z;
-      } else {
-        nxt[q] = o;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int t1 = fdiv(q[e], g.dW), x = q[e] - t1 * g.W;
+        const int t2 = fdiv(t1, g.dH), y = t1 - t2 * g.H;
+        const int b = fdiv(t2, g.dD), z = t2 - b * g.D;
+        bb[e] = b;
+        cb[e] = cur + (size_t)b * g.DHW;
+        footprint((float)z + v[e].x, (float)y + v[e].y, (float)x + v[e].z, g, f[e]);
+        gather8(cb[e], f[e], u[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float4 r = blend8(f[e], u[e]);
+        const float4 o = make_float4(v[e].x + r.x, v[e].y + r.y, v[e].z + r.z, 0.f);
+        if (has[e]) {
+          if (last) {
+            const int p = q[e] - bb[e] * g.DHW;
+            float* ob = out + (size_t)bb[e] * 3 * g.DHW + p;
+            ob[0] = o.x; ob[g.DHW] = o.y; ob[2 * g.DHW] = o.z;
+          } else {
+            nxt[q[e]] = o;
+          }
+        }
       }
     }
     if (!last) grid.sync();
@@ -309,14 +363,18 @@ __global__ void __launch_bounds__(512) vecint_fwd_fast_kernel(const float* __res
 // three rotating float4 gradient buffers G[0..2] (work): step j reads G[j%3], reduces into G[(j+1)%3] (zero on entry)
 // and zeroes G[(j+2)%3] for the step after.
 __global__ void __launch_bounds__(512) vecint_bwd_fast_kernel(const float* __restrict__ gout, const float4* __restrict__ states,
-                                                              float* __restrict__ grad_vel, float4* G, VecFast g, int nsteps, float scale) {
+                                                              float* __restrict__ grad_vel, float4* G, VecFast g, int nsteps, float scale, int dbg) {
   cg::grid_group grid = cg::this_grid();
-  const int tid0 = blockIdx.x * blockDim.x + threadIdx.x;
-  const int stride = gridDim.x * blockDim.x;
+  // voxel walk: grid-stride (default), or — dbg & 2, profiling A/B — a contiguous run of 512-voxel blocks per CTA
+  const int nblk = (g.nvox + 511) >> 9;
+  const bool contig = dbg & 2;
+  const int tid0 = contig ? (((int)((long long)blockIdx.x * nblk / gridDim.x)) << 9) + (int)threadIdx.x : (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  const int stride = contig ? 512 : (int)(gridDim.x * blockDim.x);
+  const int qend = contig ? min(g.nvox, ((int)((long long)(blockIdx.x + 1) * nblk / gridDim.x)) << 9) : g.nvox;
   float4* G0 = G;
   float4* G1 = G + (size_t)g.nvox;
   float4* G2 = G + 2 * (size_t)g.nvox;
-  for (int q = tid0; q < g.nvox; q += stride) {
+  for (int q = tid0; q < qend; q += stride) {
     const int b = q / g.DHW, p = q - b * g.DHW;
     const float* gb = gout + (size_t)b * 3 * g.DHW + p;
     G0[q] = make_float4(__ldg(gb), __ldg(gb + g.DHW), __ldg(gb + 2 * g.DHW), 0.f);
@@ -330,8 +388,8 @@ __global__ void __launch_bounds__(512) vecint_bwd_fast_kernel(const float* __res
     float4* gc = j % 3 == 0 ? G1 : (j % 3 == 1 ? G2 : G0);
     float4* __restrict__ gz = j % 3 == 0 ? G2 : (j % 3 == 1 ? G0 : G1);
     float4 own_next = make_float4(0.f, 0.f, 0.f, 0.f), go_next = own_next;
-    if (tid0 < g.nvox) { own_next = v[tid0]; go_next = gn[tid0]; }
-    for (int q = tid0; q < g.nvox; q += stride) {
+    if (tid0 < qend) { own_next = v[tid0]; go_next = gn[tid0]; }
+    for (int q = tid0; q < qend; q += stride) {
       const int t1 = fdiv(q, g.dW), x = q - t1 * g.W;
       const int t2 = fdiv(t1, g.dH), y = t1 - t2 * g.H;
       const int b = fdiv(t2, g.dD), z = t2 - b * g.D;
@@ -339,7 +397,7 @@ __global__ void __launch_bounds__(512) vecint_bwd_fast_kernel(const float* __res
       float4* gcb = gc + (size_t)b * g.DHW;
       const float4 own = own_next;
       const float4 go = go_next;
-      if (q + stride < g.nvox) { own_next = v[q + stride]; go_next = gn[q + stride]; }   // next iteration's own data, ahead of this one's gathers
+      if (q + stride < qend) { own_next = v[q + stride]; go_next = gn[q + stride]; }   // next iteration's own data, ahead of this one's gathers
       gz[q] = make_float4(0.f, 0.f, 0.f, 0.f);
       Corner8 c;
       corners_fast((float)z + own.x, (float)y + own.y, (float)x + own.z, g, c);
@@ -388,7 +446,7 @@ __global__ void __launch_bounds__(512) vecint_bwd_fast_kernel(const float* __res
     grid.sync();
   }
   const float4* Gf = nsteps % 3 == 0 ? G0 : (nsteps % 3 == 1 ? G1 : G2);
-  for (int q = tid0; q < g.nvox; q += stride) {
+  for (int q = tid0; q < qend; q += stride) {
     const int b = q / g.DHW, p = q - b * g.DHW;
     const float4 r = Gf[q];
     float* o = grad_vel + (size_t)b * 3 * g.DHW + p;
@@ -520,7 +578,9 @@ static int vecint_bwd_fast(const float* gout, const void* states, float* grad_ve
   int grid = 0;
   rc = coop_grid_fast(vecint_bwd_fast_kernel, 512, &grid);
   if (rc) return rc;
-  void* args[] = {(void*)&gout, (void*)&sp, (void*)&grad_vel, (void*)&G, (void*)&g, (void*)&nsteps, (void*)&scale};
+  const char* de = getenv("VXM_B200_VECINT_DBG");
+  int dbg = de ? atoi(de) : 0;
+  void* args[] = {(void*)&gout, (void*)&sp, (void*)&grad_vel, (void*)&G, (void*)&g, (void*)&nsteps, (void*)&scale, (void*)&dbg};
   VXM_CUDA(cudaLaunchCooperativeKernel((void*)vecint_bwd_fast_kernel, dim3(grid), dim3(512), args, 0, st));
   return check_launch("vecint_bwd");
 }
