@@ -194,6 +194,9 @@ int vxm_conv3d_tcs_supported(int Ca, int Cb, int Cout);
 size_t vxm_conv3d_tcs_pack_desc_bytes(void);
 int vxm_conv3d_tcs_pack_desc(void* desc_host, const float* w, void* wpk, int Cout, int Cin, int kd, int coutp, int transposed,
                              int begin);
+/* descriptor of a kd-folded 2-D operand of the 3-D weight w (Cout, Cin, 3, 3, 3): operand input channel kd * r + c is tap kd of
+ * real channel c, r = Cin (Cout when transposed), 3 r <= 16; packed size = vxm_conv3d_tcs_packed_bytes(3 r, coutp, 1) */
+int vxm_conv3d_tcs_pack_desc_fold(void* desc_host, const float* w, void* wpk, int Cout, int Cin, int coutp, int transposed, int begin);
 int vxm_conv3d_tcs_pack_multi(const void* descs_dev, int ndesc, int total, void* stream);
 int vxm_conv3d_tcs_fwd(const void* xa, const void* xb, const void* wpk, const float* bias, void* out, const void* mask,
                        int B, int D, int H, int W, int Ca, int Cb, int up, int Cout, int coutp, int kd, int out_mode,
@@ -236,6 +239,12 @@ int vxm_conv3d_tc_wgrad2_partial(const void* xa, const void* xb, const void* gz,
                                  size_t work_bytes, size_t* work_used, void* descs_host, int* ndesc, int B, int D, int H, int W,
                                  int Ca, int Cb, int up, int Cin_real, int Cg, int Cout_real, int kd, int accumulate, void* stream);
 int vxm_conv3d_tc_wgrad2_flush(const void* descs_host, int ndesc, void* stream);
+/* Weight gradient of a "kd-folded" layer (vxm_planar_fold_kd_bf16): x (B,D,H,W,Cx) against gz (B,D,H,W,Cg), Cx, Cg in {8,16}, as
+ * a 2-D problem per slice with the kh taps stacked in the MMA's M; grad_w has the 2-D layout (Cout_real, Cin_real, 1, 3, 3).
+ * Deferred like vxm_conv3d_tc_wgrad2_partial (one pending reduction). */
+int vxm_conv3d_tc_wgrad2_partial_khm(const void* x, const void* gz, float* grad_w, float* grad_b, void* work, size_t work_bytes,
+                                     size_t* work_used, void* descs_host, int* ndesc, int B, int D, int H, int W, int Cx,
+                                     int Cin_real, int Cg, int Cout_real, int accumulate, void* stream);
 /* ---- channels-last bf16 glue of the tensor-core U-Net engine (reference networks.py:126-138 and its autograd) ----
  * All tensors bf16 (B,D,H,W,C), C % 8 == 0.  (Dc,Hc,Wc) are the COARSE dims; the fine tensor is (fd*Dc, 2Hc, 2Wc)
  * with fd = 2 for nd == 3 and 1 for nd == 2. */
@@ -251,6 +260,11 @@ int vxm_unpool_combine_ndhwc_bf16(const void* e_fine, const void* g_skip_fine, c
  * channels are zero.  Feeds the fp32 images / the fp32 flow gradient to the tensor-core kernels. */
 int vxm_planar_to_ndhwc8_bf16(const float* const* planes, const long long* bstrides, int nplanes, void* out, int B,
                               size_t V, void* stream);
+/* kd folded into the channels: out (B,D,HW,cout) bf16, cout in {8,16}, channel kd * nplanes + p = planes[p] at slice d + kd - 1
+ * (zero outside the volume), kd = 0..2; 3 * nplanes <= cout.  A 3-D convolution with so few real input channels then runs as a
+ * 2-D one over the folded tensor (reference layers: the first ConvBlock, networks.py:122-130, and the flow head's autograd). */
+int vxm_planar_fold_kd_bf16(const float* const* planes, const long long* bstrides, int nplanes, void* out, int B, int D,
+                            size_t HW, int cout, void* stream);
 /* split-precision variants: out_hi = bf16(x), out_lo = bf16(x - out_hi); MaxPool(2) of a (hi, lo) pair tensor (the
  * maximum is taken on hi + lo, the winning child's pair is copied) */
 int vxm_planar_to_ndhwc8_split_bf16(const float* const* planes, const long long* bstrides, int nplanes, void* out_hi,

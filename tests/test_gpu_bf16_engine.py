@@ -302,3 +302,31 @@ def test_full_size_step_vs_oracle(cuda, monkeypatch, engine):
           % (engine, e_flow, e_moved, e_loss, float(loss), float(lc), gerr[len(gerr) // 2], gerr[-1]))
     assert e_flow <= tol["flow"] and e_moved <= tol["moved"] and e_loss <= tol["loss"]
     assert gerr[len(gerr) // 2] <= tol["grad_med"] and gerr[-1] <= tol["grad_max"]
+
+
+def test_kd_folded_layers_match_unfolded_step(vxm_bf16, cuda, monkeypatch):
+    """The kd-folded first convolution / flow-head backward compute the same sums as the 3-D kernels (other MMA grouping only)."""
+    import voxelmorph_b200 as vxm
+    from oracle import cases
+    shape = (16, 32, 32)
+    s, t = cases.volume_pair(5, shape, sigma=1.5)
+    S, T = torch.from_numpy(s).to(cuda), torch.from_numpy(t).to(cuda)
+    res = {}
+    for fold in ("1", "0"):
+        monkeypatch.setenv("VXM_B200_KDFOLD", fold)
+        torch.manual_seed(3)
+        model = vxm.networks.VxmDense(inshape=shape).to(cuda).train()
+        with torch.no_grad():
+            model.flow.weight.normal_(0, 2e-2)
+        y, flow = model(S, T)
+        loss = vxm.losses.NCC().loss(T, y) + 0.01 * vxm.losses.Grad("l2", loss_mult=2).loss(None, flow)
+        loss.backward()
+        torch.cuda.synchronize()
+        res[fold] = (flow.detach().cpu(), {n: p.grad.detach().cpu().clone() for n, p in model.named_parameters() if p.grad is not None})
+    f1, g1 = res["1"]
+    f0, g0 = res["0"]
+    assert float((f1 - f0).abs().max()) <= 2e-3 * float(f0.abs().max())
+    assert set(g1) == set(g0)
+    for n in g0:
+        den = float(g0[n].abs().max()) + 1e-12
+        assert float((g1[n] - g0[n]).abs().max()) <= 2e-2 * den, n

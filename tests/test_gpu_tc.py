@@ -306,3 +306,76 @@ def test_tma_and_lean_epilogue_match_reference_paths(tc, cuda, monkeypatch, shap
     assert torch.isfinite(ref).all() and float(ref.abs().max()) > 0
     for k, v in outs.items():
         assert torch.equal(v, ref), k      # same MMAs in the same order, same fp32 epilogue arithmetic: bit-identical
+
+
+# ---- round 2: kd folded into the channels (first convolution / flow head) ----
+
+def _khm_wgrad(tc, x, gz, cin_real, cout_real, cuda):
+    batch = tc.WgradBatch.get(cuda)
+    batch.reset()
+    gw = torch.empty((cout_real, cin_real, 1, 3, 3), dtype=torch.float32, device=cuda)
+    gb = torch.empty(cout_real, dtype=torch.float32, device=cuda)
+    batch.add_khm(x, gz, gw, gb, cin_real, cout_real)
+    batch.flush()
+    torch.cuda.synchronize()
+    return gw.cpu(), gb.cpu()
+
+
+@pytest.mark.parametrize("shape", [(6, 16, 34), (9, 13, 35)])
+def test_kd_folded_first_layer(tc, cuda, shape):
+    """Two image planes: fold -> 2-D convolution == the 3-D convolution; 2-D kh-in-M weight gradient == autograd."""
+    g = torch.Generator().manual_seed(31)
+    B, P, Cout = 2, 2, 16
+    x = bf(torch.randn((B, P) + shape, generator=g))
+    w = bf(torch.randn((Cout, P, 3, 3, 3), generator=g) * 0.2)
+    b = torch.randn(Cout, generator=g) * 0.1
+    xd = x.double().requires_grad_(False)
+    wd = w.double().requires_grad_(True)
+    pre = F.conv3d(xd, wd, b.double(), padding=1)
+    ref = F.leaky_relu(pre, 0.2)
+    planes = [x[:, i:i + 1].to(cuda).contiguous() for i in range(P)]
+    x3 = tc.planar_fold_kd(planes, 8)
+    assert tuple(x3.shape) == (B,) + shape + (8,)
+    # the folded tensor itself: channel kd * P + p = plane p shifted by kd - 1 slices, zero outside
+    xs = F.pad(x, (0, 0, 0, 0, 1, 1))
+    for kd in range(3):
+        for p in range(P):
+            assert torch.equal(x3[..., kd * P + p].float().cpu(), xs[:, p, kd:kd + shape[0]])
+    assert float(x3[..., 3 * P:].abs().max()) == 0.0
+    wpk, cp = tc.pack_weights_fold(w.to(cuda))
+    out = tc.conv_fwd_t(x3, None, wpk, cp, b.to(cuda), Cout, 1, slope=0.2)
+    torch.cuda.synchronize()
+    assert rel_err(tc.from_ndhwc(out).cpu(), ref) <= 1e-2
+    # weight / bias gradient
+    gy = bf(torch.randn((B, Cout) + shape, generator=g))
+    pre.backward(gy.double())
+    gw2, gb = _khm_wgrad(tc, x3, tc.to_ndhwc_bf16(gy.to(cuda)), 3 * P, Cout, cuda)
+    gw = gw2.view(Cout, 3, P, 3, 3).permute(0, 2, 1, 3, 4)
+    assert rel_err(gw, wd.grad) <= 2e-3
+    assert rel_err(gb, gy.double().sum(dim=(0, 2, 3, 4))) <= 2e-3
+
+
+@pytest.mark.parametrize("shape", [(6, 16, 34), (9, 13, 35)])
+def test_kd_folded_flow_head_backward(tc, cuda, shape):
+    """Flow head 16 -> 3: the flow gradient folded over kd gives the masked dgrad (2-D convolution) and the weight gradient."""
+    g = torch.Generator().manual_seed(32)
+    B, Cin, nd = 1, 16, 3
+    x = bf(torch.randn((B, Cin) + shape, generator=g))
+    w = bf(torch.randn((nd, Cin, 3, 3, 3), generator=g) * 0.1)
+    gy = bf(torch.randn((B, nd) + shape, generator=g))          # bf16-exact flow gradient: both paths see the same operands
+    xd = x.double().requires_grad_(True)
+    wd = w.double().requires_grad_(True)
+    F.conv3d(xd, wd, None, padding=1).backward(gy.double())
+    below = x                                                     # the layer below is LeakyReLU(0.2): derivative from its output's sign
+    refg = xd.grad * torch.where(below.double() < 0, 0.2, 1.0)
+    planes = [gy[:, i:i + 1].to(cuda).float().contiguous() for i in range(nd)]
+    g3 = tc.planar_fold_kd(planes, 16)
+    wpk, cp = tc.pack_weights_fold(w.to(cuda), transposed=True)
+    xn = tc.to_ndhwc_bf16(x.to(cuda))
+    dg = tc.conv_fwd_t(g3, None, wpk, cp, None, Cin, 1, slope=0.2, mask=xn)
+    torch.cuda.synchronize()
+    assert rel_err(tc.from_ndhwc(dg).cpu(), refg) <= 1e-2
+    gw2, gb2 = _khm_wgrad(tc, xn, g3, Cin, 3 * nd, cuda)
+    gw = gw2.view(3, nd, Cin, 3, 3).flip(0).permute(1, 2, 0, 3, 4)
+    assert rel_err(gw, wd.grad) <= 2e-3
+    assert rel_err(gb2[nd:2 * nd], gy.double().sum(dim=(0, 2, 3, 4))) <= 2e-3

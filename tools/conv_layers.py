@@ -59,6 +59,27 @@ def build():
         cout = 3 if cg == 8 else cg
         cin = 2 if cx == 8 else cx
         L[name] = (lambda xx=xx, g=g, cin=cin, cout=cout, up=up: tc.conv_wgrad(xx, None, g, cin, cout, 3, up=up))
+    # kd-folded variants of the two layers with 2 / 3 real channels on one side
+    planes2 = [torch.rand((1, 1) + FULL, device=dev) for _ in range(2)]
+    planes3 = [torch.randn((1, 1) + FULL, device=dev) for _ in range(3)]
+    L["fold: planar_fold_kd x (2 planes -> 8ch)"] = lambda: tc.planar_fold_kd(planes2, 8)
+    L["fold: planar_fold_kd g (3 planes -> 16ch)"] = lambda: tc.planar_fold_kd(planes3, 16)
+    L["plain: planar_to_ndhwc8 (3 planes)"] = lambda: tc.planar_to_ndhwc8(planes3)
+    x3 = tc.planar_fold_kd(planes2, 8)
+    W0 = w(16, 2); pk0, cp0 = tc.pack_weights_fold(W0); b16 = torch.zeros(16, device=dev)
+    L["fold: enc0_fwd 2D (6 of 8)->16"] = lambda: tc.conv_fwd_t(x3, None, pk0, cp0, b16, 16, 1, slope=0.2)
+    g3 = tc.planar_fold_kd(planes3, 16)
+    Wf = w(3, 16); pkf, cpf = tc.pack_weights_fold(Wf, transposed=True); m16 = rnd(FULL, 16)
+    L["fold: flow_dgrad 2D (9 of 16)->16 mask"] = lambda: tc.conv_fwd_t(g3, None, pkf, cpf, None, 16, 1, slope=0.2, mask=m16)
+    batch = tc.WgradBatch.get(dev)
+    gw0 = torch.empty((16, 6, 1, 3, 3), device=dev); gb0 = torch.empty(16, device=dev); gz16 = rnd(FULL, 16)
+    gwf = torch.empty((9, 16, 1, 3, 3), device=dev); gbf = torch.empty(9, device=dev); x16 = rnd(FULL, 16)
+
+    def khm(x, g, gw, gb, ci, co):
+        batch.add_khm(x, g, gw, gb, ci, co)
+        batch.flush()
+    L["fold: enc0_wgrad khm"] = lambda: khm(x3, gz16, gw0, gb0, 6, 16)
+    L["fold: flow_wgrad khm"] = lambda: khm(x16, g3, gwf, gbf, 16, 9)
     return L
 
 

@@ -59,6 +59,7 @@ SIGNATURES = {
     "vxm_conv3d_tcs_supported": (c_i, [c_i] * 3),
     "vxm_conv3d_tcs_pack_desc_bytes": (c_sz, []),
     "vxm_conv3d_tcs_pack_desc": (c_i, [c_f, c_f, c_f] + [c_i] * 6),
+    "vxm_conv3d_tcs_pack_desc_fold": (c_i, [c_f, c_f, c_f] + [c_i] * 5),
     "vxm_conv3d_tcs_pack_multi": (c_i, [c_f, c_i, c_i, c_f]),
     "vxm_conv3d_tcs_fwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f] + [c_i] * 11 + [c_fl, c_f, c_i, c_f]),
     "vxm_conv3d_tcs2_fwd": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f] + [c_i] * 11 + [c_fl, c_f, c_i, c_f]),
@@ -70,11 +71,13 @@ SIGNATURES = {
     "vxm_conv3d_tc_wgrad2_partial_bytes": (c_sz, [c_i]),
     "vxm_conv3d_tc_wgrad2_partial": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_sz, c_f, c_f, c_f] + [c_i] * 12 + [c_f]),
     "vxm_conv3d_tc_wgrad2_flush": (c_i, [c_f, c_i, c_f]),
+    "vxm_conv3d_tc_wgrad2_partial_khm": (c_i, [c_f, c_f, c_f, c_f, c_f, c_sz, c_f, c_f, c_f] + [c_i] * 9 + [c_f]),
     "vxm_pool2_ndhwc_bf16": (c_i, [c_f, c_f] + [c_i] * 6 + [c_f]),
     "vxm_sumpool_mask_ndhwc_bf16": (c_i, [c_f, c_f, c_f] + [c_i] * 6 + [c_fl, c_f]),
     "vxm_unpool_combine_ndhwc_bf16": (c_i, [c_f, c_f, c_f, c_f] + [c_i] * 6 + [c_fl, c_f]),
     "vxm_planar_to_ndhwc8_bf16": (c_i, [c_f, c_f, c_i, c_f, c_i, c_sz, c_f]),
     "vxm_planar_to_ndhwc8_split_bf16": (c_i, [c_f, c_f, c_i, c_f, c_f, c_i, c_sz, c_f]),
+    "vxm_planar_fold_kd_bf16": (c_i, [c_f, c_f, c_i, c_f, c_i, c_i, c_sz, c_i, c_f]),
     "vxm_pool2_split_ndhwc_bf16": (c_i, [c_f, c_f, c_f, c_f] + [c_i] * 6 + [c_f]),
     "vxm_planar_channel_sums": (c_i, [c_f, c_f, c_f, c_i, c_i, c_sz, c_f]),
     "vxm_maxpool2_fwd": (c_i, [c_f, c_f, c_f] + [c_i] * 6 + [c_f]),

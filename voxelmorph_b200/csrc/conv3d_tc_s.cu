@@ -297,11 +297,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const __grid_cons
             vx[hb] += HWp;
             if (!mine) continue;
             const bool valid = ok[hb];
-            [[maybe_unused]] uint4 mreg[EPI == 2 ? COUT / 8 : 1];
+            [[maybe_unused]] uint32_t mreg[EPI == 2 ? COUT / 16 : 1][8];
             if constexpr (EPI == 2) {
               if (valid) {
 #pragma unroll
-                for (int q = 0; q < COUT / 8; ++q) mreg[q] = __ldg(reinterpret_cast<const uint4*>(a.mask + vox * COUT) + q);
+                for (int q = 0; q < COUT / 16; ++q) ld_global_nc_v8(a.mask + vox * COUT + q * 16, mreg[q]);
               }
             }
             mbar_wait(&tfull[acc], tphase);
@@ -334,22 +334,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs_kernel(const __grid_cons
                 }
               } else if constexpr (EPI == 2) {
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                  const uint4 m4 = mreg[c0 / 8 + q];
-                  const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {                  // sign bits of the saved bf16 activations
-                    if (mw[e] & 0x8000u) v[q * 8 + 2 * e] *= slope;
-                    if (mw[e] & 0x80000000u) v[q * 8 + 2 * e + 1] *= slope;
-                  }
+                for (int e = 0; e < 8; ++e) {                    // sign bits of the saved bf16 activations
+                  const uint32_t mw = mreg[c0 / 16][e];
+                  if (mw & 0x8000u) v[2 * e] *= slope;
+                  if (mw & 0x80000000u) v[2 * e + 1] *= slope;
                 }
               }
               if (valid) {
                 __nv_bfloat16* dst = (EPI == 3 && c0 >= c1) ? reinterpret_cast<__nv_bfloat16*>(a.out2) + vox * (COUT - c1) + (c0 - c1)
                                                             : reinterpret_cast<__nv_bfloat16*>(a.out) + vox * c1 + c0;
                 uint4* op = reinterpret_cast<uint4*>(dst);
-                op[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-                op[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+                st_global_v8(op, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]),
+                             pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
               }
             }
           }
@@ -536,6 +532,10 @@ struct PackDesc {
   __nv_bfloat16* out;
   int Cout, Cin, KD, COUT, NN, G0, G1, transposed;
   int begin, count;      // global element range [begin, begin + count)
+  // fold > 0: `w` is a 3-D (Cout, Cin, 3, 3, 3) weight whose kd taps are folded into the input channels of a 2-D operand
+  // (KD = 1 here): operand input channel kd * fold + c <-> (tap kd, real channel c), fold = real channel count of the
+  // operand's input side (Cin forward, Cout transposed)
+  int fold;
 };
 __global__ void pack_weights_multi_kernel(const PackDesc* __restrict__ descs, int ndesc, int total) {
   for (int gi = blockIdx.x * blockDim.x + threadIdx.x; gi < total; gi += gridDim.x * blockDim.x) {
@@ -551,7 +551,14 @@ __global__ void pack_weights_multi_kernel(const PackDesc* __restrict__ descs, in
     const int kd = st / 3, kh = st % 3, g = n / d.COUT, co = n % d.COUT;
     const int tap = (kd * 3 + kh) * 3 + g;
     float v = 0.f;
-    if (!d.transposed) {
+    if (d.fold) {
+      const int fk = ci / d.fold, c = ci % d.fold;              // folded kd tap, real input channel of the operand
+      const int tap3 = (fk * 3 + kh) * 3 + g;
+      if (fk < 3) {
+        if (!d.transposed) { if (co < d.Cout) v = d.w[((size_t)co * d.Cin + c) * 27 + tap3]; }
+        else if (co < d.Cin) v = d.w[((size_t)c * d.Cin + co) * 27 + (26 - tap3)];
+      }
+    } else if (!d.transposed) {
       if (co < d.Cout && ci < d.Cin) v = d.w[((size_t)co * d.Cin + ci) * T + tap];
     } else {
       if (co < d.Cin && ci < d.Cout) v = d.w[((size_t)ci * d.Cin + co) * T + (T - 1 - tap)];
@@ -632,9 +639,24 @@ extern "C" int vxm_conv3d_tcs_pack_desc(void* desc_host, const float* w, void* w
   groups_of(cin_eff <= 8 ? 8 : (cin_eff <= 16 ? 16 : (cin_eff <= 32 ? 32 : (cin_eff <= 48 ? 48 : 64))), &g0, &g1);
   PackDesc d;
   d.w = w; d.out = (__nv_bfloat16*)wpk; d.Cout = Cout; d.Cin = Cin; d.KD = kd; d.COUT = coutp; d.NN = 3 * coutp; d.G0 = g0; d.G1 = g1;
-  d.transposed = transposed; d.begin = begin; d.count = kd * 3 * d.NN * (g0 + g1);
+  d.transposed = transposed; d.begin = begin; d.count = kd * 3 * d.NN * (g0 + g1); d.fold = 0;
   memcpy(desc_host, &d, sizeof(d));
   return d.count;      // elements of this operand (>= 0), so the caller can chain `begin`
+}
+
+// Descriptor of a kd-folded 2-D operand of the 3-D weight w (Cout, Cin, 3, 3, 3): the operand has 3 * (Cin | Cout if
+// transposed) input channels (padded to 8 / 16) and kd = 1; packed size = vxm_conv3d_tcs_packed_bytes(3 * that, coutp, 1).
+extern "C" int vxm_conv3d_tcs_pack_desc_fold(void* desc_host, const float* w, void* wpk, int Cout, int Cin, int coutp, int transposed, int begin) {
+  VXM_REQUIRE(desc_host && w && wpk && Cout > 0 && Cin > 0 && (coutp == 16 || coutp == 32), "conv3d_tcs_pack_desc_fold: bad argument");
+  const int real_in = transposed ? Cout : Cin, nout = transposed ? Cin : Cout;
+  VXM_REQUIRE(3 * real_in <= 16 && nout <= coutp, "conv3d_tcs_pack_desc_fold: %d x 3 input channels / %d outputs do not fit", real_in, nout);
+  int g0, g1;
+  groups_of(3 * real_in <= 8 ? 8 : 16, &g0, &g1);
+  PackDesc d;
+  d.w = w; d.out = (__nv_bfloat16*)wpk; d.Cout = Cout; d.Cin = Cin; d.KD = 1; d.COUT = coutp; d.NN = 3 * coutp; d.G0 = g0; d.G1 = g1;
+  d.transposed = transposed; d.begin = begin; d.count = 3 * d.NN * (g0 + g1); d.fold = real_in;
+  memcpy(desc_host, &d, sizeof(d));
+  return d.count;
 }
 
 extern "C" int vxm_conv3d_tcs_pack_multi(const void* descs_dev, int ndesc, int total, void* stream) {

@@ -373,11 +373,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs2_kernel(const __grid_con
             if (!mine) continue;
             const uint32_t taddr = tlane + acc * (uint32_t)NN;
             const bool valid = ok[hb];
-            [[maybe_unused]] uint4 mreg[COUT / 8];
+            [[maybe_unused]] uint32_t mreg[COUT / 16][8];
             if constexpr (EPI == 2) {
               if (valid) {
 #pragma unroll
-                for (int q = 0; q < COUT / 8; ++q) mreg[q] = __ldg(reinterpret_cast<const uint4*>(a.mask + o) + q);
+                for (int q = 0; q < COUT / 16; ++q) ld_global_nc_v8(a.mask + o + q * 16, mreg[q]);
               }
             }
             if (wq == 0) VXM_TR(3 + grp, etr, 0);
@@ -413,20 +413,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs2_kernel(const __grid_con
                 }
               } else {
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                  const uint4 m4 = mreg[c0 / 8 + q];
-                  const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {                  // sign bits of the saved bf16 activations
-                    if (mw[e] & 0x8000u) v[q * 8 + 2 * e] *= slope;
-                    if (mw[e] & 0x80000000u) v[q * 8 + 2 * e + 1] *= slope;
-                  }
+                for (int e = 0; e < 8; ++e) {                    // sign bits of the saved bf16 activations
+                  const uint32_t mw = mreg[c0 / 16][e];
+                  if (mw & 0x8000u) v[2 * e] *= slope;
+                  if (mw & 0x80000000u) v[2 * e + 1] *= slope;
                 }
               }
               if (valid) {
                 uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + o + c0);
-                op[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-                op[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+                st_global_v8(op, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]),
+                             pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
               }
             }
             if (wq == 0) VXM_TR(3 + grp, etr, 3);
@@ -621,7 +617,7 @@ extern "C" int vxm_conv3d_tcs2_fwd(const void* xa, const void* xb, const void* w
   int epi = 0;
   {
     const char* e = getenv("VXM_B200_TCS_EPI");       // "0": generic epilogue everywhere (A/B switch)
-    const bool plain = kd == 3 && out_mode == 0 && !out2 && Cout == coutp && !(e && e[0] == '0');
+    const bool plain = out_mode == 0 && !out2 && Cout == coutp && !(e && e[0] == '0');
     if (plain && !mask && slope >= 0.f && slope <= 1.f) epi = 1;
     else if (plain && mask && !bias) epi = 2;
   }
@@ -632,8 +628,8 @@ extern "C" int vxm_conv3d_tcs2_fwd(const void* xa, const void* xb, const void* w
   } while (0)
 #define VXM_TCS2_LAUNCH(KD_, G0_, G1_, CO_)                                                                                    \
   do {                                                                                                                        \
-    if (KD_ == 3 && epi == 1) VXM_TCS2_LAUNCH_E(3, G0_, G1_, CO_, 1);                                                          \
-    else if (KD_ == 3 && epi == 2) VXM_TCS2_LAUNCH_E(3, G0_, G1_, CO_, 2);                                                     \
+    if (epi == 1) VXM_TCS2_LAUNCH_E(KD_, G0_, G1_, CO_, 1);                                                                    \
+    else if (epi == 2) VXM_TCS2_LAUNCH_E(KD_, G0_, G1_, CO_, 2);                                                               \
     else VXM_TCS2_LAUNCH_E(KD_, G0_, G1_, CO_, 0);                                                                             \
   } while (0)
 #define VXM_TCS2_G(KD_, CO_)                                                                                                  \

@@ -61,17 +61,23 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
                : "r"(taddr) : "memory");
 }
 
-template <int KD, int G, int GOUT>
+// KHM ("kh in M", KD == 1 only): the three kh taps become three MN atoms of the A operand ONE TILE ROW (32 voxel rows) apart —
+// the same Toeplitz trick the B operand plays for kw — so a (tile, slice) costs 8 MMAs with one accumulator instead of 24
+// with three.  Used for the layers whose kd taps are folded into the channels of one operand (first layer: 2 image planes
+// x 3 slices; flow head: 3 flow-gradient planes x 3 slices), i.e. exactly the layers that otherwise pad 2 or 3 real
+// channels to 16.
+template <int KD, int G, int GOUT, bool KHM = false>
 __global__ void __launch_bounds__(NTHREADS, 1) wgrad2_kernel(const Wgrad2Args a) {
+  static_assert(!KHM || (KD == 1 && G == 16), "kh-in-M needs a 2-D operand with 16-channel rows");
   constexpr int WA = 2 * G, WG = 2 * GOUT;                  // row bytes
   constexpr uint32_t XSLAB = XROWS * WA, GSLAB = GSROWS * WG;
-  constexpr int MM = (KD * G > 64) ? 128 : 64;
+  constexpr int MM = (KD * G > 64) ? 128 : 64;              // KHM: M = (kh, ci) = 48 -> 64
   constexpr int NN = 3 * GOUT;
   constexpr int NMIRROR = KD == 3 ? 2 : 0, NPADSLAB = KD == 3 ? 1 : 0;
   constexpr int T = KD * 9;
   constexpr int KX = XROWS * (G / 8) / NLOADER, KG = GROWS * (GOUT / 8) / NLOADER;
   static_assert(XROWS * (G / 8) % NLOADER == 0 && GROWS * (GOUT / 8) % NLOADER == 0, "loader tables");
-  constexpr uint32_t need_cols = MM == 128 ? 3 * NN : 2 * NN;
+  constexpr uint32_t need_cols = KHM ? NN : (MM == 128 ? 3 * NN : 2 * NN);
   constexpr uint32_t tmem_cols = need_cols <= 128 ? 128u : (need_cols <= 256 ? 256u : 512u);
 
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -194,9 +200,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad2_kernel(const Wgrad2Args a)
           tc_fence_after();
           const uint32_t a_start = x_u32 + hslot * XSLAB;
           const uint32_t b_start = g_u32 + gs * GSLAB + (uint32_t)(GPAD - 1) * WG;
-          const uint64_t adesc0 = make_desc_mn_swz<WA>(a_start, KD == 3 ? XSLAB : 0u, 0u);
+          const uint64_t adesc0 = make_desc_mn_swz<WA>(a_start, KHM ? (uint32_t)(TWR * WA) : (KD == 3 ? XSLAB : 0u), 0u);
           const uint64_t bdesc0 = make_desc_mn_swz<WG>(b_start, (uint32_t)WG, 0u);   // base offset 0: the swizzle is a function of the absolute address (verified on B200: the matrix-base-offset form gives wrong sums)
-          if (elect_one()) {
+          if (KHM) {
+            if (elect_one()) {
+#pragma unroll
+              for (int i = 0; i < GROWS / 16; ++i) {
+                const uint64_t adesc = adesc0 + (uint64_t)(((16 * i) * WA) >> 4);
+                const uint64_t bdesc = bdesc0 + (uint64_t)((16 * i * WG) >> 4);
+                umma_f16(tmem_base, adesc, bdesc, idesc, i == 0 ? acc0 : 1u);
+              }
+              umma_commit(&xempty[hslot]);
+              umma_commit(&gempty[gs]);
+            }
+          } else if (elect_one()) {
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh) {
               const uint32_t tmem_d = MM == 128 ? tmem_base + (uint32_t)(kh * NN)
@@ -278,7 +295,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad2_kernel(const Wgrad2Args a)
     if (has_work) {
       mbar_wait(done, 0);
       tc_fence_after();
-      if (MM == 128) {
+      if (KHM) {
+        // accumulator row m = kh * 16 + ci on TMEM lane (m % 16) + 32 * (m / 16): warp = kh, lanes 0..15 = ci; columns q * GOUT + co
+        const int kh = warp, ci = lane & 15;
+#pragma unroll 1
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+          for (int c0 = 0; c0 < GOUT; c0 += 8) {
+            uint32_t r[8];
+            tmem_ld8(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(q * GOUT + c0), r);
+            tmem_ld_wait();
+            if (kh < 3 && lane < 16) {
+              const int tap = kh * 3 + (2 - q);
+              float4* o = reinterpret_cast<float4*>(part + ((size_t)tap * G + ci) * GOUT + c0);
+              o[0] = make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
+              o[1] = make_float4(__uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
+            }
+          }
+      } else if (MM == 128) {
         // accumulator row m = kd * G + ci on TMEM lane m; columns kh * NN + q * GOUT + co, q = 2 - kw
         const int m = warp * 32 + lane, kd = m / G, ci = m % G;
 #pragma unroll 1
@@ -436,7 +470,7 @@ bool wgrad2_supported(int Ca, int Cb, int Cg) {
 // one source tensor (C channels, optionally nearest-x2 upsampled) against gz; weights [ci_off, ci_off + ci_cnt) of Cin_total
 int wgrad2_launch(const void* x, int Cx, int up, const void* gz, int Cg, float* grad_w, float* grad_b, void* work, int B, int D, int H, int W,
                   int kd, int Cout_real, int Cin_total, int ci_off, int ci_cnt, int accumulate, cudaStream_t st, ReduceDesc* defer,
-                  size_t* work_used) {
+                  size_t* work_used, bool khm) {
   Wgrad2Args a{};
   a.x = (const __nv_bfloat16*)x; a.Cx = Cx; a.up = up; a.upd = (up && kd == 3) ? 1 : 0;
   a.gz = (const __nv_bfloat16*)gz; a.Cg = Cg;
@@ -486,7 +520,11 @@ int wgrad2_launch(const void* x, int Cx, int up, const void* gz, int Cg, float* 
     if (G == 16 && GOUT == 16) VXM_W2_LAUNCH(KD_, 16, 16); else if (G == 16) VXM_W2_LAUNCH(KD_, 16, 32);                     \
     else if (GOUT == 16) VXM_W2_LAUNCH(KD_, 32, 16); else VXM_W2_LAUNCH(KD_, 32, 32);                                        \
   } while (0)
-  if (kd == 3) VXM_W2_G(3); else VXM_W2_G(1);
+  if (khm) {
+    VXM_REQUIRE(kd == 1 && G == 16 && GOUT == 16 && !up, "conv3d_tc_wgrad2 (kh in M): needs kd = 1 and at most 16 channels on both sides");
+    VXM_CUDA(cudaFuncSetAttribute(wgrad2_kernel<1, 16, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    wgrad2_kernel<1, 16, 16, true><<<grid, NTHREADS, smem, st>>>(a);
+  } else if (kd == 3) VXM_W2_G(3); else VXM_W2_G(1);
   int rc = check_launch("conv3d_tc_wgrad2");
   if (rc) return rc;
   const int T = kd * 9, per_cta = T * G * GOUT;
@@ -530,7 +568,7 @@ extern "C" int vxm_conv3d_tc_wgrad2_partial(const void* xa, const void* xb, cons
   char* wp = (char*)work;
   if (Ca) {
     const int cnt = Cin_real < Ca ? Cin_real : Ca;
-    int rc = wgrad2_launch(xa, Ca, up, gz, Cg, grad_w, grad_b, wp, B, D, H, W, kd, Cout_real, Cin_real, 0, cnt, accumulate, st, &d[*ndesc], &used);
+    int rc = wgrad2_launch(xa, Ca, up, gz, Cg, grad_w, grad_b, wp, B, D, H, W, kd, Cout_real, Cin_real, 0, cnt, accumulate, st, &d[*ndesc], &used, false);
     if (rc) return rc;
     VXM_REQUIRE(used <= work_bytes, "conv3d_tc_wgrad2_partial: workspace too small");
     ++*ndesc; wp += used; total += used;
@@ -538,12 +576,32 @@ extern "C" int vxm_conv3d_tc_wgrad2_partial(const void* xa, const void* xb, cons
   if (Cb && Cin_real > Ca) {
     const int cnt = Cin_real - Ca < Cb ? Cin_real - Ca : Cb;
     int rc = wgrad2_launch(xb, Cb, 0, gz, Cg, grad_w, Ca ? nullptr : grad_b, wp, B, D, H, W, kd, Cout_real, Cin_real, Ca, cnt, accumulate, st,
-                           &d[*ndesc], &used);
+                           &d[*ndesc], &used, false);
     if (rc) return rc;
     VXM_REQUIRE(total + used <= work_bytes, "conv3d_tc_wgrad2_partial: workspace too small");
     ++*ndesc; total += used;
   }
   *work_used = total;
+  return VXM_OK;
+}
+
+// Weight gradient of a kd-folded layer (see vxm_planar_fold_kd_bf16): x (B, D, H, W, Cx <= 16) against gz (B, D, H, W, Cg <= 16) as a
+// 2-D problem per slice with the kh taps stacked in M.  grad_w receives the 2-D layout (Cout_real, Cin_real, 1, 3, 3).
+extern "C" int vxm_conv3d_tc_wgrad2_partial_khm(const void* x, const void* gz, float* grad_w, float* grad_b, void* work, size_t work_bytes,
+                                                size_t* work_used, void* descs_host, int* ndesc, int B, int D, int H, int W, int Cx,
+                                                int Cin_real, int Cg, int Cout_real, int accumulate, void* stream) {
+  VXM_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && x && gz && grad_w && work && work_used && descs_host && ndesc, "conv3d_tc_wgrad2_partial_khm: bad argument");
+  VXM_REQUIRE((Cx == 8 || Cx == 16) && (Cg == 8 || Cg == 16), "conv3d_tc_wgrad2_partial_khm: channel counts (%d | %d) unsupported", Cx, Cg);
+  VXM_REQUIRE(Cin_real > 0 && Cin_real <= Cx && Cout_real > 0 && Cout_real <= Cg, "conv3d_tc_wgrad2_partial_khm: real channel counts out of range");
+  VXM_REQUIRE(*ndesc + 1 <= MAXRED, "conv3d_tc_wgrad2_partial_khm: too many pending reductions (flush first)");
+  ReduceDesc* d = (ReduceDesc*)descs_host;
+  size_t used = 0;
+  int rc = wgrad2_launch(x, Cx, 0, gz, Cg, grad_w, grad_b, work, B, D, H, W, 1, Cout_real, Cin_real, 0, Cin_real, accumulate, as_stream(stream),
+                         &d[*ndesc], &used, true);
+  if (rc) return rc;
+  VXM_REQUIRE(used <= work_bytes, "conv3d_tc_wgrad2_partial_khm: workspace too small");
+  ++*ndesc;
+  *work_used = used;
   return VXM_OK;
 }
 

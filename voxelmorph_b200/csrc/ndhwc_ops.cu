@@ -182,6 +182,45 @@ __global__ void __launch_bounds__(256) planar_to_ndhwc8_kernel(PlanarSrc src, __
   }
 }
 
+// "kd folded into the channels": out[b][d][hw][kd * n + p] = plane_p[b][d + kd - 1][hw] (0 outside the volume), kd = 0..2,
+// channels >= 3n zero; COUT = 8 or 16.  A 3-D convolution with n <= COUT / 3 real input channels becomes a 2-D one over the
+// folded tensor (3 instead of 9 MMA steps per tile), see engine_bf16.py.
+template <int COUT>
+__global__ void __launch_bounds__(256) planar_fold_kd_kernel(PlanarSrc src, __nv_bfloat16* __restrict__ out, int D, int HW) {
+  // grid = (HW / 256, D, B): no index divisions, 32-bit offsets inside one (batch item, slice)
+  const int hw = blockIdx.x * 256 + threadIdx.x;
+  if (hw >= HW) return;
+  const int d = blockIdx.y, b = blockIdx.z;
+  float r[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) r[c] = 0.f;
+#pragma unroll
+  for (int p = 0; p < COUT / 3; ++p) {
+    if (p < src.n) {
+      const float* q = src.p[p] + (size_t)b * src.bstride[p] + (size_t)d * HW + hw;
+      if (d > 0) r[p] = __ldg(q - HW);
+      r[src.n + p] = __ldg(q);
+      if (d + 1 < D) r[2 * src.n + p] = __ldg(q + HW);
+    }
+  }
+  __nv_bfloat16* o = out + (((size_t)b * D + d) * HW + hw) * COUT;
+  if constexpr (COUT == 16) {     // one 256-bit store per voxel: whole sectors
+    uint32_t w[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(r[2 * e], r[2 * e + 1]);
+      w[e] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]),
+                 "r"(w[6]), "r"(w[7]) : "memory");
+  } else {
+    V8 t;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) t.v[e] = r[e];
+    st8(o, t);
+  }
+}
+
 // split-precision (bf16x3) variants: a value is carried as a bf16 pair hi = bf16(x), lo = bf16(x - hi)  (16 mantissa bits)
 __global__ void __launch_bounds__(256) planar_to_ndhwc8_split_kernel(PlanarSrc src, __nv_bfloat16* __restrict__ out_hi,
                                                                      __nv_bfloat16* __restrict__ out_lo, int B, size_t V) {
@@ -295,6 +334,20 @@ extern "C" int vxm_planar_to_ndhwc8_bf16(const float* const* planes, const long 
   size_t cap = (size_t)sm_count() * 16;
   planar_to_ndhwc8_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, as_stream(stream)>>>(src, (__nv_bfloat16*)out, B, V);
   return check_launch("planar_to_ndhwc8");
+}
+
+extern "C" int vxm_planar_fold_kd_bf16(const float* const* planes, const long long* bstrides, int nplanes, void* out, int B, int D,
+                                       size_t HW, int cout, void* stream) {
+  VXM_REQUIRE(planes && bstrides && out && nplanes > 0 && B > 0 && D > 0 && HW > 0, "planar_fold_kd: bad argument");
+  VXM_REQUIRE((cout == 8 || cout == 16) && 3 * nplanes <= cout, "planar_fold_kd: %d planes x 3 do not fit %d channels", nplanes, cout);
+  PlanarSrc src{};
+  src.n = nplanes;
+  for (int i = 0; i < nplanes; ++i) { src.p[i] = planes[i]; src.bstride[i] = bstrides[i]; }
+  VXM_REQUIRE(D <= 65535 && B <= 65535 && HW < (1u << 30), "planar_fold_kd: volume exceeds the launch grid limits");
+  const dim3 grid((unsigned)((HW + 255) / 256), (unsigned)D, (unsigned)B);
+  if (cout == 8) planar_fold_kd_kernel<8><<<grid, 256, 0, as_stream(stream)>>>(src, (__nv_bfloat16*)out, D, (int)HW);
+  else planar_fold_kd_kernel<16><<<grid, 256, 0, as_stream(stream)>>>(src, (__nv_bfloat16*)out, D, (int)HW);
+  return check_launch("planar_fold_kd");
 }
 
 extern "C" int vxm_planar_to_ndhwc8_split_bf16(const float* const* planes, const long long* bstrides, int nplanes, void* out_hi,

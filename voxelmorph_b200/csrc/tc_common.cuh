@@ -166,6 +166,19 @@ __host__ __device__ inline uint32_t make_idesc_bf16(int M, int N, int a_mn_major
   return d;
 }
 
+// 256-bit global accesses (sm_100: LDG.256 / STG.256): one instruction moves a lane's 16 bf16 channels, and a warp's store
+// covers whole 32-byte sectors instead of two half-sector passes.  `p` must be 32-byte aligned.
+__device__ __forceinline__ void st_global_v8(void* p, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint32_t r4, uint32_t r5, uint32_t r6,
+                                             uint32_t r7) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(r4), "r"(r5), "r"(r6), "r"(r7)
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_v8(const void* p, uint32_t (&r)[8]) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

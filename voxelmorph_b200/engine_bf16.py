@@ -54,10 +54,28 @@ class _PackPlan:
         self.params = [c.weight for c in convs]
         dev = self.params[0].device
         dsz = int(lib.vxm_conv3d_tcs_pack_desc_bytes())
-        host = ctypes.create_string_buffer(dsz * 2 * len(convs))
+        host = ctypes.create_string_buffer(dsz * (2 * len(convs) + 2))
         self.table = {}
         self.keep = []
         n, begin = 0, 0
+        # kd-folded 2-D operands (tc.planar_fold_kd): forward of the first convolution, dgrad of the flow head
+        for w, transposed in ((self.params[0], False), (self.params[-1], True)):
+            if w.dim() != 5 or w.shape[2] != 3:
+                continue
+            Cout, Cin = w.shape[0], w.shape[1]
+            real_in, nout = (Cout, Cin) if transposed else (Cin, Cout)
+            if 3 * real_in > (16 if transposed else 8) or nout not in (8, 16, 32):
+                continue
+            coutp = 16 if nout <= 16 else 32
+            out = torch.empty(int(lib.vxm_conv3d_tcs_packed_bytes(3 * real_in, coutp, 1)) // 2, dtype=torch.bfloat16, device=dev)
+            cnt = lib.vxm_conv3d_tcs_pack_desc_fold(ctypes.cast(ctypes.addressof(host) + n * dsz, ctypes.c_void_p), _lib.ptr(w), _lib.ptr(out),
+                                                    Cout, Cin, coutp, 1 if transposed else 0, begin)
+            if cnt <= 0:
+                continue
+            self.table[(id(w), transposed, "fold")] = (out, (coutp, "s"))
+            self.keep.append(out)
+            begin += cnt
+            n += 1
         for li, w in enumerate(self.params):
             w5 = w if w.dim() == 5 else w.unsqueeze(2)
             Cout, Cin, kd = w5.shape[0], w5.shape[1], w5.shape[2]
@@ -95,6 +113,9 @@ class _PackPlan:
 
     def lookup(self, w, transposed):
         return self.table.get((id(w), transposed))
+
+    def lookup_fold(self, w, transposed):
+        return self.table.get((id(w), transposed, "fold"))
 
 
 def _plan_of(model):
@@ -170,7 +191,7 @@ def _unpool_combine(e_fine, g_skip, g_pool, nd, slope):
 class _Conv:
     """One convolution of the tape: inputs, output, parameters."""
     __slots__ = ("w", "b", "planar", "xa", "xb", "up", "out", "slope", "cin", "cout", "a_id", "b_id", "out_id", "planar_out",
-                 "xa_lo", "xb_lo")
+                 "xa_lo", "xb_lo", "fold")
 
 
 def _run_conv_split(cv, kd):
@@ -190,6 +211,10 @@ def _run_conv(cv, kd, plan=None):
     """Forward of one tape entry."""
     ca = 0 if cv.xa is None else cv.xa.shape[-1]
     cb = 0 if cv.xb is None else cv.xb.shape[-1]
+    if cv.fold == "x":
+        # kd folded into the input channels: a 2-D convolution per slice (3 instead of 9 MMA steps per tile)
+        wpk, cp = plan.lookup_fold(cv.w, False)
+        return tc.conv_fwd_t(cv.xa, None, wpk, cp, cv.b.detach() if cv.b is not None else None, cv.cout, 1, slope=cv.slope)
     if cv.planar is None and tc.use_t_kernel(ca, cb, cv.cout):
         hit = plan.lookup(cv.w, False) if (plan is not None and tc._use_s(ca, cb, cv.cout)) else None
         wpk, cp = hit if hit is not None else _cache.get(cv.w, "fwd_t", lambda: tc.pack_weights_t(cv.w.detach()))
@@ -234,6 +259,7 @@ def forward_tape(model, source, target, split=False):
         cv.a_id, cv.b_id = a_id, b_id
         cv.xa_lo = lows.get(a_id) if split else None
         cv.xb_lo = lows.get(b_id) if split else None
+        cv.fold = "x" if (a_id is not None and producer.get(a_id) == "input" and fold_first) else None
         if not planar_out:
             _check_cout(cv.cout, "a U-Net convolution output")
         if planar is None:
@@ -241,7 +267,7 @@ def forward_tape(model, source, target, split=False):
             cb = 0 if cv.xb is None else cv.xb.shape[-1]
             first_layer = cv.xa is not None and producer.get(a_id) == "input"
             if first_layer:
-                if ca != 8 or cb or cv.cin > 8:
+                if ca != 8 or cb or cv.cin > 8 or (cv.fold == "x" and 3 * cv.cin > 8):
                     raise _lib.VxmError("bf16 engine: the first convolution takes at most 8 input feature planes")
             elif ca + cb != cv.cin or (ca + cb) % 16 or ca + cb > 64:
                 raise _lib.VxmError("bf16 engine: unsupported convolution input channels %d (+%d); need a multiple of 16, at most 64"
@@ -274,8 +300,13 @@ def forward_tape(model, source, target, split=False):
 
     # the fp32 images enter as one bf16 channels-last tensor with 8 channels (src planes, trg planes, zeros)
     cur = new_id()
+    first_w = unet.encoder[0][0].main.weight
+    fold_first = (not split and nd == 3 and tc.kdfold_enabled() and plan is not None and plan.lookup_fold(first_w, False) is not None
+                  and first_w.shape[1] == len(planes) and tc._variant() in ("auto", "s"))
     if split:
         tensors[cur], lows[cur] = tc.planar_to_ndhwc8_split(planes)
+    elif fold_first:
+        tensors[cur] = tc.planar_fold_kd(planes, 8)      # (kd, plane) channels: the first convolution runs as 2-D
     else:
         tensors[cur] = tc.planar_to_ndhwc8(planes)
     producer[cur] = "input"
@@ -330,6 +361,7 @@ def backward_tape(ctx, g_flow):
     gskip = {}    # encoder-output id -> raw skip gradient
     grads = {}
     dev = g_flow.device
+    folded = []   # (conv, gw2d, gb2d, kind): 2-D weight gradients of the kd-folded layers, mapped back after the flush
     for entry in reversed(tape):
         if entry[0] == "pool":
             _, in_id, out_id = entry
@@ -337,11 +369,32 @@ def backward_tape(ctx, g_flow):
             gz[in_id] = _unpool_combine(e, gskip.pop(in_id, None), graw.pop(out_id), nd, _slope_of(ctx, in_id))
             continue
         cv = entry[1]
+        fold_g = (cv.planar_out and nd == 3 and tc.kdfold_enabled() and plan is not None and plan.lookup_fold(cv.w, True) is not None
+                  and cv.xb is None and not cv.up and cv.xa is not None and cv.xa.shape[-1] in (8, 16) and cv.xa.shape[-1] == cv.cin
+                  and producer.get(cv.a_id) == "conv" and tc._variant() in ("auto", "s"))
+        if fold_g:
+            # flow head, kd folded into the channels of the flow gradient: (kd', component) = 9 of 16 channels
+            g_in = tc.planar_fold_kd([g_flow[:, i:i + 1] for i in range(g_flow.shape[1])], 16)
+            gwf = torch.empty((3 * nd, cv.cin, 1, 3, 3), dtype=torch.float32, device=dev)
+            gbf = torch.empty(3 * nd, dtype=torch.float32, device=dev) if cv.b is not None else None
+            batch.add_khm(cv.xa, g_in, gwf, gbf, cv.cin, 3 * nd)
+            folded.append((cv, gwf, gbf, "g"))
+            t = cv.a_id
+            wpk, cp = plan.lookup_fold(cv.w, True)
+            gz[t] = tc.conv_fwd_t(g_in, None, wpk, cp, None, cv.cin, 1, slope=_slope_of(ctx, t), mask=tensors[t])
+            continue
         if cv.planar_out:
             # flow head: the fp32 planar flow gradient becomes an 8-channel bf16 channels-last tensor
             g_in = tc.planar_to_ndhwc8([g_flow[:, i:i + 1] for i in range(g_flow.shape[1])])
         else:
             g_in = gz.pop(cv.out_id)
+        if cv.fold == "x":
+            # first layer over the kd-folded images: 2-D weight gradient with kh in M, no dgrad
+            gwf = torch.empty((cv.cout, 3 * cv.cin, 1, 3, 3), dtype=torch.float32, device=dev)
+            gbf = torch.empty(cv.cout, dtype=torch.float32, device=dev) if cv.b is not None else None
+            batch.add_khm(cv.xa, g_in, gwf, gbf, 3 * cv.cin, cv.cout)
+            folded.append((cv, gwf, gbf, "x"))
+            continue
         # parameters whose .grad is a view of FusedAdam's flat gradient buffer (optim.FlatParams marks them)
         # are accumulated into directly by the reduce kernel; autograd then receives no gradient for them
         direct = (getattr(cv.w, "_vxm_flat_grad", False) and cv.w.grad is not None and cv.w.grad.is_contiguous()
@@ -388,6 +441,23 @@ def backward_tape(ctx, g_flow):
             del g_up
             gskip[cv.b_id] = g_sk
     batch.flush()     # one launch reduces every layer's per-CTA partials (fixed order: deterministic)
+    for cv, gwf, gbf, kind in folded:
+        if kind == "x":      # gwf[co][kd * P + p][0][kh][kw] -> gw[co][p][kd][kh][kw]
+            gw = gwf.view(cv.cout, 3, cv.cin, 3, 3).permute(0, 2, 1, 3, 4)
+            gb = gbf
+        else:                # gwf[kd' * nd + c][ci][0][kh][kw] -> gw[c][ci][2 - kd'][kh][kw]; the unshifted copy (kd' = 1) sums to the bias gradient
+            gw = gwf.view(3, nd, cv.cin, 3, 3).flip(0).permute(1, 2, 0, 3, 4)
+            gb = None if gbf is None else gbf[nd:2 * nd]
+        direct = (getattr(cv.w, "_vxm_flat_grad", False) and cv.w.grad is not None
+                  and (cv.b is None or (getattr(cv.b, "_vxm_flat_grad", False) and cv.b.grad is not None)))
+        if direct:
+            cv.w.grad.add_(gw)
+            if cv.b is not None:
+                cv.b.grad.add_(gb)
+        else:
+            grads[cv.w] = gw.contiguous()
+            if cv.b is not None:
+                grads[cv.b] = gb.contiguous()
     return grads
 
 

@@ -149,6 +149,47 @@ def planar_to_ndhwc8(planes):
     return out
 
 
+def kdfold_enabled():
+    """kd-folded execution of the two layers with 2 / 3 real channels on one side (VXM_B200_KDFOLD=0: A/B switch)."""
+    import os
+    return os.environ.get("VXM_B200_KDFOLD", "1") != "0"
+
+
+def planar_fold_kd(planes, cout):
+    """<= cout/3 planar fp32 (B,1,D,H,W) volumes -> bf16 (B,D,H,W,cout) with channel kd * n + p = plane p at slice d + kd - 1
+    (zero outside the volume): the kd taps of a 3-D convolution folded into the channels (csrc/ndhwc_ops.cu)."""
+    lib = _lib.load()
+    ref = planes[0]
+    B, D, H, W = ref.shape[0], ref.shape[-3], ref.shape[-2], ref.shape[-1]
+    n = len(planes)
+    arr_p = (ctypes.c_void_p * 8)(*([p.data_ptr() for p in planes] + [0] * (8 - n)))
+    arr_s = (ctypes.c_longlong * 8)(*([p.stride(0) for p in planes] + [0] * (8 - n)))
+    out = torch.empty((B, D, H, W, cout), dtype=torch.bfloat16, device=ref.device)
+    _lib.check(lib.vxm_planar_fold_kd_bf16(arr_p, arr_s, n, _lib.ptr(out), B, D, H * W, cout, _lib.stream_ptr()), "vxm_planar_fold_kd_bf16")
+    return out
+
+
+def pack_weights_fold(w, transposed=False):
+    """Packed kd-folded 2-D operand of the 3-D weight w (Cout, Cin, 3, 3, 3) (see vxm_conv3d_tcs_pack_desc_fold).
+    Returns (tensor, (coutp, "s")).  Stand-alone helper (tests / tools); the engine packs through its _PackPlan."""
+    lib = _lib.load()
+    w = w.contiguous()
+    Cout, Cin = w.shape[0], w.shape[1]
+    real_in, nout = (Cout, Cin) if transposed else (Cin, Cout)
+    coutp = 16 if nout <= 16 else 32
+    nbytes = int(lib.vxm_conv3d_tcs_packed_bytes(3 * real_in, coutp, 1))
+    out = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
+    dsz = int(lib.vxm_conv3d_tcs_pack_desc_bytes())
+    host = ctypes.create_string_buffer(dsz)
+    cnt = lib.vxm_conv3d_tcs_pack_desc_fold(ctypes.cast(host, ctypes.c_void_p), _lib.ptr(w), _lib.ptr(out), Cout, Cin, coutp, 1 if transposed else 0, 0)
+    if cnt <= 0:
+        raise _lib.VxmError("vxm_conv3d_tcs_pack_desc_fold: %s" % _lib.last_error())
+    descs = torch.frombuffer(bytearray(host.raw), dtype=torch.uint8).to(w.device)
+    _lib.check(lib.vxm_conv3d_tcs_pack_multi(_lib.ptr(descs), 1, cnt, _lib.stream_ptr()), "vxm_conv3d_tcs_pack_multi")
+    torch.cuda.current_stream(w.device).synchronize()       # `descs` must outlive the launch
+    return out, (coutp, "s")
+
+
 # ---- weights-stationary ("transposed") kernel: Cin in {8,16,32,48}, Cout <= 32 -------------------------------------
 
 def _variant():
@@ -350,6 +391,21 @@ class WgradBatch:
                                                     ctypes.byref(self.used), ctypes.cast(self.host, ctypes.c_void_p), ctypes.byref(self.n),
                                                     B, D, H, W, Ca, Cb, 1 if up else 0, cin, Cg, cout, kd, 1 if accumulate else 0,
                                                     _lib.stream_ptr()), "vxm_conv3d_tc_wgrad2_partial")
+        self.off += int(self.used.value)
+
+    def add_khm(self, x, gz, gw2d, gb, cin_real, cout_real):
+        """Weight gradient of a kd-folded layer: x (B,D,H,W,Cx) against gz (B,D,H,W,Cg) -> gw2d (cout_real, cin_real, 1, 3, 3)
+        (overwritten at flush), gb (cout_real) or None."""
+        lib = _lib.load()
+        need = int(lib.vxm_conv3d_tc_wgrad2_partial_bytes(1))
+        if self.off + need > self.WORK_BYTES or self.n.value + 1 > self.maxn:
+            self.flush()
+        B, D, H, W, Cg = gz.shape
+        _lib.check(lib.vxm_conv3d_tc_wgrad2_partial_khm(_lib.ptr(x), _lib.ptr(gz), _lib.ptr(gw2d), _lib.ptr(gb),
+                                                        ctypes.c_void_p(self.work.data_ptr() + self.off), self.WORK_BYTES - self.off,
+                                                        ctypes.byref(self.used), ctypes.cast(self.host, ctypes.c_void_p), ctypes.byref(self.n),
+                                                        B, D, H, W, x.shape[-1], cin_real, Cg, cout_real, 0, _lib.stream_ptr()),
+                   "vxm_conv3d_tc_wgrad2_partial_khm")
         self.off += int(self.used.value)
 
     def reset(self):
