@@ -8,6 +8,7 @@
 // channels are split into at most two groups of 16 / 32 / 64 channels (48 = 32 + 16), each with its own slab region.
 // A (kd, kh) tap shifts the A operand by whole 32-voxel rows (a multiple of the 8-row swizzle period), so the start
 // address stays pattern-aligned and the descriptor base offset is 0.
+#include <stdlib.h>
 #include <string.h>
 
 #include "tc_common.cuh"
@@ -18,7 +19,7 @@ namespace tcs {
 using namespace vxm::tc;
 
 constexpr int WT = 32, WUSE = 30;      // tile: HT (4 or 8) rows x 32 columns (30 written), slab = (HT + 2) x 32 voxel rows
-constexpr int MAXSLOT = 8, MAXACC = 4;
+constexpr int MAXSLOT = 16, MAXACC = 4;
 constexpr int NLOADER = 96, NTHREADS = 512, NGRP = 3;   // warps 0-3 epilogue group 0, 4 MMA issuer, 5-7 loader, 8-11 / 12-15 epilogue groups 1 / 2
 
 struct ConvSArgs {
@@ -740,7 +741,14 @@ static int conv_tcs_launch(const void* xa, const void* xb, const void* wpk, cons
   a.nitems = (int)(tiles * a.nchunks);
   const size_t slab = (size_t)(HTv + 2) * WT * (g0 + g1) * 2;
   int nslot = (int)((227 * 1024 - fixed) / slab);
-  if (nslot > MAXSLOT) nslot = MAXSLOT;
+  {
+    // ring depth: the slabs of up to 13 steps ahead (16-channel layers) hide the L2 / HBM latency of the tensor copies — with 8
+    // slots the issuers waited ~550 clk per step for slab data (profiles/r2_conv_ablation.md).  VXM_B200_RING=8: A/B switch.
+    const char* e = getenv("VXM_B200_RING");
+    const int cap = e ? atoi(e) : MAXSLOT;
+    if (nslot > cap) nslot = cap;
+    if (nslot > MAXSLOT) nslot = MAXSLOT;
+  }
   VXM_REQUIRE(nslot >= 4, "conv3d_tcs_fwd: not enough shared memory for the slab ring");
   a.nslot = nslot;
   size_t smem = fixed + (size_t)nslot * slab;

@@ -31,7 +31,7 @@ namespace tcs2 {
 using namespace vxm::tc;
 
 constexpr int WT = 32, WUSE = 30;      // tile: HT (4 or 8) rows x 32 columns (30 written), slab = (HT + 2) x 32 voxel rows
-constexpr int MAXSLOT = 8, MAXACC = 6;
+constexpr int MAXSLOT = 16, MAXACC = 6;
 constexpr int NLOADER = 64, NTHREADS = 512;   // warps 0-3 epilogue group 0, 4 / 5 MMA issuers (even / odd steps), 6-7 loader, 8-11 / 12-15 epilogue groups 1 / 2
 
 struct ConvSArgs {
@@ -348,6 +348,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs2_kernel(const __grid_con
       const uint32_t tlane = tmem_base + ((uint32_t)(wq * 32) << 16);
       uint32_t etr = 0;
       const size_t slice = (size_t)a.H * a.W * COUT;            // elements per output slice
+      const int c1 = (EPI == 3 && a.out2) ? a.csplit : COUT;    // EPI 3: channels [0, c1) -> out, [c1, COUT) -> out2
       for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
         const int wt = item % a.tiles_w, ht = (item / a.tiles_w) % a.tiles_h;
         const int ch = (item / HW_tiles) % a.nchunks, b = item / (HW_tiles * a.nchunks);
@@ -411,7 +412,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs2_kernel(const __grid_con
                   const float x = v[c] + bs[c0 + c];
                   v[c] = fmaxf(x, x * slope);                    // LeakyReLU for 0 <= slope <= 1
                 }
-              } else {
+              } else if constexpr (EPI == 2) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {                    // sign bits of the saved bf16 activations
                   const uint32_t mw = mreg[c0 / 16][e];
@@ -420,7 +421,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tcs2_kernel(const __grid_con
                 }
               }
               if (valid) {
-                uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + o + c0);
+                // o = voxel index * COUT; EPI 3 splits the channels between two tensors of c1 and COUT - c1 channels
+                __nv_bfloat16* op = (EPI == 3 && c0 >= c1) ? reinterpret_cast<__nv_bfloat16*>(a.out2) + o / COUT * (COUT - c1) + (c0 - c1)
+                                                           : reinterpret_cast<__nv_bfloat16*>(a.out) + (EPI == 3 ? o / COUT * c1 : o) + c0;
                 st_global_v8(op, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]),
                              pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
               }
@@ -556,7 +559,7 @@ extern "C" int vxm_conv3d_tcs2_fwd(const void* xa, const void* xb, const void* w
                                    float slope, void* out2, int csplit, void* stream) {
   VXM_REQUIRE(B > 0 && D > 0 && H > 4 && W > 0 && wpk && out, "conv3d_tcs2_fwd: bad argument");
   VXM_REQUIRE(kd == 1 || kd == 3, "conv3d_tcs2_fwd: kd must be 1 or 3");
-  VXM_REQUIRE(coutp == 16 || coutp == 32, "conv3d_tcs2_fwd: padded Cout must be 16 or 32");
+  VXM_REQUIRE(coutp == 16 || coutp == 32 || (coutp == 48 && Ca + Cb == 32), "conv3d_tcs2_fwd: padded Cout must be 16 or 32 (48 for 32 input channels)");
   const int cin = Ca + Cb;
   VXM_REQUIRE(cin == 8 || cin == 16 || cin == 32 || (Ca == 32 && Cb == 16), "conv3d_tcs2_fwd: channel counts (%d,%d) unsupported", Ca, Cb);
   ConvSArgs a{};
@@ -569,7 +572,13 @@ extern "C" int vxm_conv3d_tcs2_fwd(const void* xa, const void* xb, const void* w
   const size_t fixed = ((a.wbytes + 1023u) & ~1023u) + 1024 + 512;
   const size_t slab = (size_t)10 * WT * (g0 + g1) * 2;
   int nslot = (int)((227 * 1024 - fixed) / slab);
-  if (nslot > MAXSLOT) nslot = MAXSLOT;
+  {
+    // ring depth: more slabs in flight hide the L2 / HBM latency of the tensor copies (VXM_B200_RING=8: A/B switch)
+    const char* e = getenv("VXM_B200_RING");
+    const int cap = e ? atoi(e) : MAXSLOT;
+    if (nslot > cap) nslot = cap;
+    if (nslot > MAXSLOT) nslot = MAXSLOT;
+  }
   VXM_REQUIRE(nslot >= (kd == 3 ? 5 : 3), "conv3d_tcs2_fwd: not enough shared memory for 8-row slabs");
   a.nslot = nslot;
   a.tiles_h = (H + 7) / 8; a.tiles_w = (W + WUSE - 1) / WUSE;
@@ -617,9 +626,10 @@ extern "C" int vxm_conv3d_tcs2_fwd(const void* xa, const void* xb, const void* w
   int epi = 0;
   {
     const char* e = getenv("VXM_B200_TCS_EPI");       // "0": generic epilogue everywhere (A/B switch)
-    const bool plain = out_mode == 0 && !out2 && Cout == coutp && !(e && e[0] == '0');
-    if (plain && !mask && slope >= 0.f && slope <= 1.f) epi = 1;
-    else if (plain && mask && !bias) epi = 2;
+    const bool plain = out_mode == 0 && Cout == coutp && !(e && e[0] == '0');
+    if (plain && !out2 && !mask && slope >= 0.f && slope <= 1.f) epi = 1;
+    else if (plain && !out2 && mask && !bias) epi = 2;
+    else if (plain && !mask && !bias && slope < 0.f && (!out2 || csplit % 16 == 0)) epi = 3;
   }
 #define VXM_TCS2_LAUNCH_E(KD_, G0_, G1_, CO_, E_)                                                                              \
   do {                                                                                                                        \
@@ -630,13 +640,15 @@ extern "C" int vxm_conv3d_tcs2_fwd(const void* xa, const void* xb, const void* w
   do {                                                                                                                        \
     if (epi == 1) VXM_TCS2_LAUNCH_E(KD_, G0_, G1_, CO_, 1);                                                                    \
     else if (epi == 2) VXM_TCS2_LAUNCH_E(KD_, G0_, G1_, CO_, 2);                                                               \
+    else if (epi == 3) VXM_TCS2_LAUNCH_E(KD_, G0_, G1_, CO_, 3);                                                               \
     else VXM_TCS2_LAUNCH_E(KD_, G0_, G1_, CO_, 0);                                                                             \
   } while (0)
 #define VXM_TCS2_G(KD_, CO_)                                                                                                  \
   do {                                                                                                                        \
     if (g0 == 16) VXM_TCS2_LAUNCH(KD_, 16, 0, CO_); else if (g1 == 0) VXM_TCS2_LAUNCH(KD_, 32, 0, CO_); else VXM_TCS2_LAUNCH(KD_, 32, 16, CO_); \
   } while (0)
-  if (kd == 3) { if (coutp == 16) VXM_TCS2_G(3, 16); else VXM_TCS2_G(3, 32); }
+  if (coutp == 48) { if (kd == 3) VXM_TCS2_LAUNCH(3, 32, 0, 48); else VXM_TCS2_LAUNCH(1, 32, 0, 48); }
+  else if (kd == 3) { if (coutp == 16) VXM_TCS2_G(3, 16); else VXM_TCS2_G(3, 32); }
   else { if (coutp == 16) VXM_TCS2_G(1, 16); else VXM_TCS2_G(1, 32); }
   return check_launch("conv3d_tcs2_fwd");
 }

@@ -17,6 +17,8 @@
 // All 3 (kh) x [M x 3*GOUT] fp32 accumulators stay in TMEM for the CTA's whole lifetime; each CTA writes ONE partial
 // [27][G][GOUT]; wgrad2_reduce_kernel sums the partials in fixed order (deterministic).  The otherwise idle epilogue
 // warps fold the bias gradient (sum of gz) out of the staged gz rows.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace vxm {
@@ -37,6 +39,7 @@ struct Wgrad2Args {
   float* bias_partial;                       // [grid][GOUT] or null
   int B, D, H, W;
   int tiles_h, tiles_w, dchunk, nchunks, nitems, nslot;
+  int dbg;      // profiling only (VXM_B200_WGRAD_DBG): 1 = no MMAs issued, 2 = no slab copies, 4 = no bias sums
 };
 
 __host__ __device__ inline uint32_t swz(uint32_t off, uint32_t width) { return off ^ (((off >> 7) & (width / 16 - 1)) << 4); }
@@ -157,6 +160,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad2_kernel(const Wgrad2Args a)
         for (int k = 0; k < KX; ++k) {
           const bool ok = dok && soff[k] >= 0;
           const __nv_bfloat16* src = ok ? base + soff[k] : a.x;
+          if (a.dbg & 2) continue;
           cp_async16(slab + doff[k], src, ok ? 16u : 0u);
           if (NMIRROR && xslot < (uint32_t)NMIRROR) cp_async16(slab + (size_t)NS * XSLAB + doff[k], src, ok ? 16u : 0u);
         }
@@ -171,6 +175,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad2_kernel(const Wgrad2Args a)
 #pragma unroll
           for (int k = 0; k < KG; ++k) {
             const bool ok = goff[k] >= 0;
+            if (a.dbg & 2) continue;
             cp_async16(gt + gdoff[k], ok ? baseG + goff[k] : a.gz, ok ? 16u : 0u);
           }
           cp_async_arrive_noinc(&gfull[gslot]);
@@ -206,6 +211,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad2_kernel(const Wgrad2Args a)
             if (elect_one()) {
 #pragma unroll
               for (int i = 0; i < GROWS / 16; ++i) {
+                if (a.dbg & 1) break;
                 const uint64_t adesc = adesc0 + (uint64_t)(((16 * i) * WA) >> 4);
                 const uint64_t bdesc = bdesc0 + (uint64_t)((16 * i * WG) >> 4);
                 umma_f16(tmem_base, adesc, bdesc, idesc, i == 0 ? acc0 : 1u);
@@ -216,6 +222,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad2_kernel(const Wgrad2Args a)
           } else if (elect_one()) {
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh) {
+              if (a.dbg & 1) break;
               const uint32_t tmem_d = MM == 128 ? tmem_base + (uint32_t)(kh * NN)
                                                 : tmem_base + ((uint32_t)((kh & 1) * 16) << 16) + (uint32_t)((kh >> 1) * NN);
 #pragma unroll
@@ -252,7 +259,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad2_kernel(const Wgrad2Args a)
 #pragma unroll
     for (int c = 0; c < GOUT; ++c) bsum[c] = 0.f;
     const int rowi = warp * 32 + lane;
-    if (has_work && a.bias_partial) {
+    if (has_work && a.bias_partial && !(a.dbg & 4)) {
       uint32_t gs = 0, gph = 0;
       uint32_t roff[GOUT / 8];
 #pragma unroll
@@ -476,6 +483,10 @@ int wgrad2_launch(const void* x, int Cx, int up, const void* gz, int Cg, float* 
   a.gz = (const __nv_bfloat16*)gz; a.Cg = Cg;
   a.B = B; a.D = D; a.H = H; a.W = W;
   a.tiles_h = (H + TH - 1) / TH; a.tiles_w = (W + TUSE - 1) / TUSE;
+  {
+    const char* de = getenv("VXM_B200_WGRAD_DBG");
+    a.dbg = de ? atoi(de) : 0;
+  }
   const int G = Cx <= 16 ? 16 : 32, GOUT = Cg <= 16 ? 16 : 32;
   const int nsm = sm_count();
   // depth chunking: balance the persistent CTAs (waves of nsm items) against the 2 halo slabs every chunk re-loads

@@ -221,6 +221,8 @@ def _use_s2(xa, xb, coutp, full, up, kd):
         return False
     cin = (0 if xa is None else xa.shape[-1]) + (0 if xb is None else xb.shape[-1])
     H = full.shape[2] * (2 if (xb is None and up) else 1)
+    if coutp == 48:          # the single-pass dgrad of the 48-channel concat layer (32 -> 32 + 16 channels)
+        return cin == 32 and H > 4 and os.environ.get("VXM_B200_TCS2_48", "1") == "1"
     return coutp in (16, 32) and cin in (8, 16, 32, 48) and H > 4 and not (cin == 48 and coutp == 32)
 
 
