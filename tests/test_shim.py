@@ -219,3 +219,22 @@ def test_train_loop_body_two_gpus_transparent_dp(cuda, tmp_path):
     assert a["allreduces"] == b["allreduces"] == 3                   # one gradient exchange per step
     assert abs(a["param_sum"] - b["param_sum"]) <= 1e-9 * a["param_abs"]   # replicas stay identical
     assert sorted(os.listdir(tmp_path / "m")) == ["0000.pt", "0001.pt"]     # written once (rank 0), not twice
+
+
+@pytest.mark.gpu
+def test_data_feed_never_creates_the_cuda_context(cuda, tmp_path):
+    """scripts/torch/train.py draws its first batch (:113) before it sets CUDA_VISIBLE_DEVICES (:125): importing the package and
+    drawing batches must leave CUDA uninitialised, or `--gpu N` / one process per GPU silently land on device 0."""
+    lst, _ = make_volumes(tmp_path, n=2)
+    code = ("import os, torch\n"
+            "os.environ['VXM_BACKEND'] = 'pytorch'\n"
+            "import voxelmorph as vxm\n"
+            "g = vxm.generators.scan_to_scan(vxm.py.utils.read_file_list(%r), batch_size=1, bidir=False, add_feat_axis=True)\n"
+            "a = next(g); b = next(g)\n"
+            "assert not torch.cuda.is_initialized(), 'the data feed initialised CUDA'\n"
+            "os.environ['CUDA_VISIBLE_DEVICES'] = '0'\n"
+            "x = torch.from_numpy(a[0][0]).to('cuda').float()\n"
+            "c = next(g)\n"                              # later draws may page-lock: the process has its context now
+            "print('ok', torch.cuda.device_count(), float(x.sum()))\n" % lst)
+    r = run_py(["-c", code], cwd=str(tmp_path))
+    assert r.returncode == 0 and r.stdout.startswith("ok 1 "), (r.stdout + r.stderr)[-2000:]

@@ -28,11 +28,23 @@ import numpy as np
 __all__ = ["VolumeCache", "load_volfile", "volgen", "scan_to_scan", "scan_to_atlas", "semisupervised", "Prefetcher"]
 
 
-def _pinned_empty(shape, dtype):
-    """Page-locked numpy array when a CUDA runtime is usable, plain numpy otherwise.  Returns (array, owner)."""
+def _cuda_ready():
+    """True once THIS PROCESS already has a CUDA context.  The data feed must never create one itself: the reference's
+    train.py draws its first batch (scripts/torch/train.py:113) BEFORE it sets CUDA_VISIBLE_DEVICES (train.py:125), and the CUDA
+    runtime reads that variable when it initialises — a feed that page-locks memory at the first draw (or merely asks
+    torch.cuda.is_available()) pins every rank of a multi-GPU run to device 0."""
     try:
         import torch
-        if torch.cuda.is_available():
+        return torch.cuda.is_initialized()
+    except Exception:  # noqa: BLE001
+        return False
+
+
+def _pinned_empty(shape, dtype):
+    """Page-locked numpy array when this process already uses CUDA, plain numpy otherwise.  Returns (array, owner)."""
+    try:
+        if _cuda_ready():
+            import torch
             t = torch.empty(tuple(shape), dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
             return t.numpy(), t
     except Exception:  # noqa: BLE001 - pinning is an optimisation, never a requirement
@@ -87,8 +99,8 @@ class VolumeCache:
     """Decode-once store: (source, np_var, pad_shape, resize_factor, add_feat_axis) -> ready-to-batch array.
 
     Floating-point volumes are stored as float32 (what train.py:200 converts to anyway); integer volumes (label maps)
-    keep their dtype.  `max_bytes` bounds the cache (least recently used entries are dropped); `pin=None` pins when a CUDA
-    runtime is available.
+    keep their dtype.  `max_bytes` bounds the cache (least recently used entries are dropped); `pin=None` page-locks the
+    volumes once the process has a CUDA context (never creating one: see _cuda_ready).
     """
 
     def __init__(self, max_bytes=None, pin=None):
@@ -117,6 +129,15 @@ class VolumeCache:
             if hit is not None:
                 self._items.move_to_end(key)
                 self.hits += 1
+                if (self.pin is not False and key not in self._owners and hit.dtype == np.float32 and _cuda_ready()):
+                    # decoded before the process had a CUDA context (see _cuda_ready): page-lock it now, once
+                    buf, owner = _pinned_empty(hit.shape, hit.dtype)
+                    if owner is not None:
+                        np.copyto(buf, hit)
+                        buf.setflags(write=False)
+                        self._items[key] = buf
+                        self._owners[key] = owner
+                        hit = buf
                 return hit
         vol = _decode(src, np_var)
         if pad_shape:
