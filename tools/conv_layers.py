@@ -83,6 +83,14 @@ def build():
     return L
 
 
+if sys.argv[1:2] == ["--once"]:
+    # every selected layer once (ncu replays the launch itself): `ncu --set full -k regex:"conv_tcs|wgrad2_kernel" ... tools/conv_layers.py --once`
+    for name, fn in build().items():
+        if sys.argv[2:] and not any(t in name for t in sys.argv[2:]):
+            continue
+        fn()
+    torch.cuda.synchronize()
+    sys.exit(0)
 sets = sys.argv[1:] or [""]
 L = build()
 res = {}
