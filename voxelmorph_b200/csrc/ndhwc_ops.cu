@@ -185,7 +185,9 @@ __global__ void __launch_bounds__(256) planar_to_ndhwc8_kernel(PlanarSrc src, __
 // "kd folded into the channels": out[b][d][hw][kd * n + p] = plane_p[b][d + kd - 1][hw] (0 outside the volume), kd = 0..2,
 // channels >= 3n zero; COUT = 8 or 16.  A 3-D convolution with n <= COUT / 3 real input channels becomes a 2-D one over the
 // folded tensor (3 instead of 9 MMA steps per tile), see engine_bf16.py.
-template <int COUT>
+// NP = number of planes (compile time: the channel index kd * NP + p must be a constant, a run-time index sends the
+// register array to local memory — the first version of this kernel ran at a third of the HBM rate for that reason)
+template <int COUT, int NP>
 __global__ void __launch_bounds__(256) planar_fold_kd_kernel(PlanarSrc src, __nv_bfloat16* __restrict__ out, int D, int HW) {
   // grid = (HW / 256, D, B): no index divisions, 32-bit offsets inside one (batch item, slice)
   const int hw = blockIdx.x * 256 + threadIdx.x;
@@ -195,13 +197,11 @@ __global__ void __launch_bounds__(256) planar_fold_kd_kernel(PlanarSrc src, __nv
 #pragma unroll
   for (int c = 0; c < COUT; ++c) r[c] = 0.f;
 #pragma unroll
-  for (int p = 0; p < COUT / 3; ++p) {
-    if (p < src.n) {
-      const float* q = src.p[p] + (size_t)b * src.bstride[p] + (size_t)d * HW + hw;
-      if (d > 0) r[p] = __ldg(q - HW);
-      r[src.n + p] = __ldg(q);
-      if (d + 1 < D) r[2 * src.n + p] = __ldg(q + HW);
-    }
+  for (int p = 0; p < NP; ++p) {
+    const float* q = src.p[p] + (size_t)b * src.bstride[p] + (size_t)d * HW + hw;
+    if (d > 0) r[p] = __ldg(q - HW);
+    r[NP + p] = __ldg(q);
+    if (d + 1 < D) r[2 * NP + p] = __ldg(q + HW);
   }
   __nv_bfloat16* o = out + (((size_t)b * D + d) * HW + hw) * COUT;
   if constexpr (COUT == 16) {     // one 256-bit store per voxel: whole sectors
@@ -345,8 +345,18 @@ extern "C" int vxm_planar_fold_kd_bf16(const float* const* planes, const long lo
   for (int i = 0; i < nplanes; ++i) { src.p[i] = planes[i]; src.bstride[i] = bstrides[i]; }
   VXM_REQUIRE(D <= 65535 && B <= 65535 && HW < (1u << 30), "planar_fold_kd: volume exceeds the launch grid limits");
   const dim3 grid((unsigned)((HW + 255) / 256), (unsigned)D, (unsigned)B);
-  if (cout == 8) planar_fold_kd_kernel<8><<<grid, 256, 0, as_stream(stream)>>>(src, (__nv_bfloat16*)out, D, (int)HW);
-  else planar_fold_kd_kernel<16><<<grid, 256, 0, as_stream(stream)>>>(src, (__nv_bfloat16*)out, D, (int)HW);
+  cudaStream_t st = as_stream(stream);
+  __nv_bfloat16* o = (__nv_bfloat16*)out;
+  const int hw = (int)HW;
+  switch (cout * 8 + nplanes) {
+    case 8 * 8 + 1: planar_fold_kd_kernel<8, 1><<<grid, 256, 0, st>>>(src, o, D, hw); break;
+    case 8 * 8 + 2: planar_fold_kd_kernel<8, 2><<<grid, 256, 0, st>>>(src, o, D, hw); break;
+    case 16 * 8 + 1: planar_fold_kd_kernel<16, 1><<<grid, 256, 0, st>>>(src, o, D, hw); break;
+    case 16 * 8 + 2: planar_fold_kd_kernel<16, 2><<<grid, 256, 0, st>>>(src, o, D, hw); break;
+    case 16 * 8 + 3: planar_fold_kd_kernel<16, 3><<<grid, 256, 0, st>>>(src, o, D, hw); break;
+    case 16 * 8 + 4: planar_fold_kd_kernel<16, 4><<<grid, 256, 0, st>>>(src, o, D, hw); break;
+    default: planar_fold_kd_kernel<16, 5><<<grid, 256, 0, st>>>(src, o, D, hw); break;
+  }
   return check_launch("planar_fold_kd");
 }
 
