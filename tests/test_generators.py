@@ -151,3 +151,27 @@ def test_prefetcher_preserves_order_and_propagates_errors(tmp_path):
     assert next(pf) == 1
     with pytest.raises(RuntimeError, match="decode failed"):
         next(pf)
+
+
+def test_data_feed_never_asks_for_cuda(tmp_path, monkeypatch):
+    """The reference's train.py sets CUDA_VISIBLE_DEVICES (scripts/torch/train.py:125) AFTER drawing its first batch (:113); the CUDA
+    runtime reads that variable when it initialises, so the feed must not touch it: neither torch.cuda.is_available() (which
+    initialises the driver) nor page-locked allocations before the process has a context of its own."""
+    import numpy as np
+    import torch
+    from voxelmorph_b200 import generators as G
+
+    def boom(*a, **k):
+        raise AssertionError("the data feed queried / initialised CUDA")
+    monkeypatch.setattr(torch.cuda, "is_available", boom)
+    monkeypatch.setattr(torch.cuda, "init", boom)
+    monkeypatch.setattr(torch.cuda, "is_initialized", lambda: False)
+    names = []
+    for i in range(2):
+        p = tmp_path / ("v%d.npz" % i)
+        np.savez_compressed(p, vol=np.random.default_rng(i).random((8, 10, 12)))
+        names.append(str(p))
+    g = G.scan_to_scan(names, batch_size=2, bidir=False, add_feat_axis=True)
+    (a, b), _ = next(g)
+    assert a.dtype == np.float32 and a.shape == (2, 8, 10, 12, 1) and b.shape == a.shape
+    next(g)
