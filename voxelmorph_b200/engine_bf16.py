@@ -442,12 +442,10 @@ def backward_tape(ctx, g_flow):
             gskip[cv.b_id] = g_sk
     batch.flush()     # one launch reduces every layer's per-CTA partials (fixed order: deterministic)
     for cv, gwf, gbf, kind in folded:
-        if kind == "x":      # gwf[co][kd * P + p][0][kh][kw] -> gw[co][p][kd][kh][kw]
-            gw = gwf.view(cv.cout, 3, cv.cin, 3, 3).permute(0, 2, 1, 3, 4)
-            gb = gbf
-        else:                # gwf[kd' * nd + c][ci][0][kh][kw] -> gw[c][ci][2 - kd'][kh][kw]; the unshifted copy (kd' = 1) sums to the bias gradient
-            gw = gwf.view(3, nd, cv.cin, 3, 3).flip(0).permute(1, 2, 0, 3, 4)
-            gb = None if gbf is None else gbf[nd:2 * nd]
+        if kind == "x":
+            gw, gb = unfold_grad_first(gwf, cv.cout, cv.cin), gbf
+        else:
+            gw, gb = unfold_grad_flow(gwf, gbf, nd, cv.cin)
         direct = (getattr(cv.w, "_vxm_flat_grad", False) and cv.w.grad is not None
                   and (cv.b is None or (getattr(cv.b, "_vxm_flat_grad", False) and cv.b.grad is not None)))
         if direct:
@@ -459,6 +457,46 @@ def backward_tape(ctx, g_flow):
             if cv.b is not None:
                 grads[cv.b] = gb.contiguous()
     return grads
+
+
+# ---- index algebra of the kd-folded layers (pure tensor views; checked on CPU against torch's own 3-D convolution in
+# tests/test_kdfold_algebra.py, on the GPU against the kernels in tests/test_gpu_tc.py) ----------------------------------------
+
+def fold_planes(planes):
+    """Reference (torch) form of csrc/ndhwc_ops.cu:planar_fold_kd_kernel: [(B,1,D,H,W)] * n -> (B, D, H, W, 3n), channel
+    kd * n + p = plane p at slice d + kd - 1, zero outside the volume."""
+    x = torch.cat(planes, dim=1)                                   # (B, n, D, H, W)
+    xp = torch.nn.functional.pad(x, (0, 0, 0, 0, 1, 1))            # one zero slice on either side of D
+    D = x.shape[2]
+    return torch.cat([xp[:, :, kd:kd + D] for kd in range(3)], dim=1).permute(0, 2, 3, 4, 1).contiguous()
+
+
+def fold_weight_first(w):
+    """3-D weight (Cout, P, 3, 3, 3) of the first convolution -> the 2-D weight (Cout, 3P, 3, 3) the folded tensor is convolved
+    with: input channel kd * P + p <-> (tap kd, plane p).  (What vxm_conv3d_tcs_pack_desc_fold packs, transposed = 0.)"""
+    co, p = w.shape[0], w.shape[1]
+    return w.permute(0, 2, 1, 3, 4).reshape(co, 3 * p, 3, 3)
+
+
+def fold_weight_flow_dgrad(w):
+    """3-D weight (C, Cin, 3, 3, 3) of the flow head -> the 2-D cross-correlation kernel (Cin, 3C, 3, 3) that turns the folded flow
+    gradient (channel kd' * C + c = component c at slice d + kd' - 1) into the gradient w.r.t. the head's input:
+    K[ci][kd' * C + c][kh][kw] = w[c][ci][2 - kd'][2 - kh][2 - kw].  (vxm_conv3d_tcs_pack_desc_fold, transposed = 1.)"""
+    c, ci = w.shape[0], w.shape[1]
+    return w.flip(2, 3, 4).permute(1, 2, 0, 3, 4).reshape(ci, 3 * c, 3, 3)
+
+
+def unfold_grad_first(gwf, cout, cin):
+    """2-D weight gradient (Cout, 3 Cin, 1, 3, 3) of the folded first layer -> (Cout, Cin, 3, 3, 3): gwf[co][kd * P + p] = gw[co][p][kd]."""
+    return gwf.view(cout, 3, cin, 3, 3).permute(0, 2, 1, 3, 4)
+
+
+def unfold_grad_flow(gwf, gbf, nd, cin):
+    """2-D weight gradient (3 nd, Cin, 1, 3, 3) of the flow head against the folded flow gradient -> (nd, Cin, 3, 3, 3):
+    gwf[kd' * nd + c][ci][kh][kw] = gw[c][ci][2 - kd'][kh][kw]  (x at slice d pairs with the flow gradient at d + kd' - 1, i.e.
+    the gradient at v with x at v + 1 - kd').  The bias gradient is the channel sum of the unshifted copy (kd' = 1)."""
+    gw = gwf.view(3, nd, cin, 3, 3).flip(0).permute(1, 2, 0, 3, 4)
+    return gw, (None if gbf is None else gbf[nd:2 * nd])
 
 
 def _slope_of(ctx, tid):
