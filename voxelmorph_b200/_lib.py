@@ -165,7 +165,11 @@ def reduce_workspace(device):
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     ws = _reduce_ws.get(key)
     if ws is None:
-        nbytes = int(load().vxm_reduce_workspace_bytes())
-        ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
-        _reduce_ws[key] = ws
+        lib = load()     # (takes the same lock: resolve the library first)
+        with _lock:      # nn.DataParallel (train.py:151-154) calls the replicas from one thread per GPU
+            ws = _reduce_ws.get(key)
+            if ws is None:
+                nbytes = int(lib.vxm_reduce_workspace_bytes())
+                ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+                _reduce_ws[key] = ws
     return ws

@@ -5,6 +5,7 @@ Activations of this engine are bf16, channels-last: a (B, C, D, H, W) logical te
 (Cout, Cin, 3, 3, 3)); packed bf16 copies are refreshed whenever the parameter version changes.
 """
 import ctypes
+import threading
 
 import torch
 
@@ -95,6 +96,7 @@ def _planar_args(planar):
 
 
 _wgrad_ws = {}
+_ws_lock = threading.Lock()      # workspace tables are shared by the per-GPU threads of nn.DataParallel
 
 
 def conv_wgrad(xa, xb, gz, cin, cout, kd, up=False, planar_x=None, planar_g=None, need_bias=True, out_w=None, out_b=None, batch=None):
@@ -118,8 +120,11 @@ def conv_wgrad(xa, xb, gz, cin, cout, kd, up=False, planar_x=None, planar_g=None
     key = (dev.index, torch.cuda.current_stream(dev).cuda_stream, kd)
     work = _wgrad_ws.get(key)
     if work is None:
-        work = torch.empty(int(lib.vxm_conv3d_tc_wgrad_workspace_bytes(kd)), dtype=torch.uint8, device=dev)
-        _wgrad_ws[key] = work
+        with _ws_lock:
+            work = _wgrad_ws.get(key)
+            if work is None:
+                work = torch.empty(int(lib.vxm_conv3d_tc_wgrad_workspace_bytes(kd)), dtype=torch.uint8, device=dev)
+                _wgrad_ws[key] = work
     # out_w / out_b: existing (contiguous fp32) gradient buffers to ACCUMULATE into instead of fresh tensors
     accumulate = out_w is not None
     gw = out_w if accumulate else torch.empty((cout, cin, kd, 3, 3), dtype=torch.float32, device=dev)
@@ -366,7 +371,10 @@ class WgradBatch:
         key = (device.index, torch.cuda.current_stream(device).cuda_stream)
         b = cls._cache.get(key)
         if b is None:
-            b = cls._cache[key] = cls(device)
+            with _ws_lock:
+                b = cls._cache.get(key)
+                if b is None:
+                    b = cls._cache[key] = cls(device)
         return b
 
     def __init__(self, device):
