@@ -217,12 +217,40 @@ def reference_arm(args):
 CONV_SOURCES = ("conv3d_tc_s.cu", "conv3d_tc_s2.cu", "conv3d_tc_wgrad2.cu", "tc_common.cuh")
 
 
+def _strip_comments(text):
+    """C / CUDA source without comments and blank lines (string literals respected): the hash below identifies the CODE the
+    committed ncu pass measured — rewording a comment must not invalidate it, changing a statement must."""
+    out, i, n, in_str = [], 0, len(text), False
+    while i < n:
+        c = text[i]
+        if in_str:
+            out.append(c)
+            if c == "\\" and i + 1 < n:
+                out.append(text[i + 1]); i += 1
+            elif c == '"':
+                in_str = False
+        elif c == '"':
+            in_str = True; out.append(c)
+        elif text.startswith("//", i):
+            while i < n and text[i] != "\n":
+                i += 1
+            continue
+        elif text.startswith("/*", i):
+            j = text.find("*/", i + 2)
+            i = n if j < 0 else j + 2
+            continue
+        else:
+            out.append(c)
+        i += 1
+    return "\n".join(l.strip() for l in "".join(out).splitlines() if l.strip())
+
+
 def conv_source_hash():
     import hashlib
     h = hashlib.sha256()
     for f in CONV_SOURCES:
-        with open(os.path.join(ROOT, "voxelmorph_b200", "csrc", f), "rb") as fh:
-            h.update(fh.read())
+        with open(os.path.join(ROOT, "voxelmorph_b200", "csrc", f), "r") as fh:
+            h.update(_strip_comments(fh.read()).encode())
     return h.hexdigest()[:16]
 
 

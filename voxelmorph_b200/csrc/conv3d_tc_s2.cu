@@ -1,15 +1,18 @@
-// EXPERIMENT (not compiled into libvxm_b200.so, never run on hardware yet): the kw-stacked swizzled convolution of
-// voxelmorph_b200/csrc/conv3d_tc_s.cu with TWO MMA-issuing warps that alternate whole slab steps.
+// Conv3d k=3 on tcgen05, kw-stacked swizzled formulation of conv3d_tc_s.cu with TWO MMA-issuing warps that alternate whole
+// slab steps (8-row tiles).  The default for every layer whose 8-row slab ring fits shared memory (tc.py:_use_s2; +5 % on the
+// step over the single issuer, profiles/r2_conv_layers_ab.txt); the A operand is staged by TMA tensor copies, the epilogues
+// are specialised per use (EPI), and the kernel carries the profiling switches / clock64 trace that produced
+// profiles/r2_conv_ablation.md.
 //
-// Why: ncu on the shipped kernel (profiles/r1_final_conv_ncu.md) shows the single issuer warp
-// busy in its own per-step instruction stream (~130 serial instructions: barrier polls, descriptor construction, uniform
-// datapath latencies) with the MMA queue full only 22 % of the time, while the tensor pipe idles 48 % (thin layers) /
-// 25 % (48->32).  Giving each of two issuers every other step doubles the time an issuer has per step.  (Splitting one
-// step's two tile halves between two issuers was tried on hardware and bought nothing: both kept the per-step work.)
+// Why two issuers: ncu on the single-issuer kernel (profiles/r1_final_conv_ncu.md) showed the issuer warp busy in its own
+// per-step instruction stream (~130 serial instructions: barrier polls, descriptor construction, uniform datapath latencies)
+// while the tensor pipe idled 48 % (thin layers) / 25 % (48->32).  Giving each of two issuers every other step doubles the time
+// an issuer has per step.  (Splitting one step's two tile halves between two issuers bought nothing: both kept the per-step
+// work; issuing the two halves interleaved is slower — round 2, measured.)
 //
-// Protocol (8-row tiles, 3 accumulators, 3 epilogue groups as in the shipped kernel):
+// Protocol (8-row tiles, 3 or 6 accumulators, 3 epilogue groups as in the single-issuer kernel):
 //   * step t (global counter over the CTA's lifetime) belongs to issuer t & 1; it produces events 2t, 2t+1 (tile halves),
-//     event e uses accumulator e % 3 and is drained by epilogue group e % 3;
+//     event e uses accumulator e % NACC (NACC = 3 or 6) and is drained by epilogue group e % 3;
 //   * full[slot]  : both issuers walk ALL slabs in order with their own (slot, phase) cursor;
 //   * empty[slot] : two arrivals, exactly ONE FROM EACH ISSUER, each made after that issuer has observed the slab's
 //                   full phase and after its last MMA that reads the slab was issued: own step j arrives on slabs j and
@@ -17,10 +20,9 @@
 //                   the item the would-be owner of step nd arrives on slabs nd and nd+1, the other one on slab nd+1.
 //                   (A slot can therefore not be refilled before both cursors have passed it: no parity aliasing.)
 //   * tfull[acc]  : one commit per event, consumed phase by phase by the owning epilogue group;
-//   * tempty[issuer][acc] : the group that drains event e signals the issuer of event e+3 (the next user of that
-//                   accumulator), which waits for it before issuing e+3; every barrier has one waiter, consecutive phases.
-// To try it: copy this file into voxelmorph_b200/csrc/, declare vxm_conv3d_tcs2_fwd in include/vxm_b200.h + _lib.py (same
-// signature as vxm_conv3d_tcs_fwd; weights packed by vxm_conv3d_tcs_pack) and route tc.conv_fwd_t to it.
+//   * tempty[issuer][acc] : the group that drains event e signals the issuer of event e+NACC (the next user of that
+//                   accumulator), which waits for it before issuing it; every barrier has one waiter, consecutive phases.
+// Entry point: vxm_conv3d_tcs2_fwd (same signature as vxm_conv3d_tcs_fwd; weights packed by vxm_conv3d_tcs_pack*).
 #include <stdlib.h>
 
 #include "tc_common.cuh"
